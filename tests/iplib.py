@@ -1,0 +1,125 @@
+"""ctypes front end shared by the oracle and the product library.
+
+Both export the reference's bind(c) argument lists (src/ipolates.F90:587-636 etc.); only the
+symbol prefix differs ("oracle_" for oracle/_build/libip_oracle.so, "" for the product's
+libipb200.so), and every symbol carries the build-kind suffix _4 / _d / _8.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+KINDS = {"4": (np.float32, np.int32), "d": (np.float64, np.int32), "8": (np.float64, np.int64)}
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class IpLib:
+    def __init__(self, path, prefix, kind):
+        self.lib = C.CDLL(path)
+        self.prefix = prefix
+        self.kind = kind
+        self.R, self.I = KINDS[kind]
+        self.cI = C.c_int32 if self.I == np.int32 else C.c_int64
+        self.cR = C.c_float if self.R == np.float32 else C.c_double
+
+    def fn(self, name):
+        f = getattr(self.lib, f"{self.prefix}{name}_{self.kind}")
+        f.restype = None
+        return f
+
+    def _ia(self, v, n=None):
+        a = np.ascontiguousarray(np.asarray(v, dtype=self.I).ravel())
+        if n is not None:
+            assert a.size == n, (a.size, n)
+        return a
+
+    def _grid_args(self, desc):
+        if desc[0] == "grib2":
+            t = self._ia(desc[2])
+            return [_p(self._ia([desc[1]])), _p(t), _p(self._ia([t.size]))], [t]
+        k = self._ia(desc[1], 200)
+        return [_p(k)], [k]
+
+    def ipolates(self, ip, ipopt, gin, gout, mi, mo, km, ibi, li, gi, no=0, rlat=None, rlon=None, out_init=None):
+        """Returns dict(no, rlat, rlon, ibo, lo, go, iret).  gi: [km, mi] C-order (== Fortran GI(MI,KM))."""
+        assert gin[0] == gout[0]
+        R = self.R
+        gi = np.ascontiguousarray(gi, dtype=R).reshape(km, mi)
+        li = np.ascontiguousarray(li, dtype=np.uint8).reshape(km, mi)
+        rlat = np.zeros(mo, R) if rlat is None else np.ascontiguousarray(rlat, dtype=R).copy()
+        rlon = np.zeros(mo, R) if rlon is None else np.ascontiguousarray(rlon, dtype=R).copy()
+        fillv = -7777.0 if out_init is None else out_init
+        go = np.full((km, mo), fillv, R)
+        lo = np.full((km, mo), 7, np.uint8)
+        ibo = self._ia([-7] * km)
+        no_a, iret = self._ia([no]), self._ia([-7])
+        a_in, keep1 = self._grid_args(gin)
+        a_out, keep2 = self._grid_args(gout)
+        sc = [self._ia([ip]), self._ia(ipopt, 20), self._ia([mi]), self._ia([mo]), self._ia([km]), self._ia(ibi, km)]
+        name = "ipolates_grib2" if gin[0] == "grib2" else "ipolates_grib1"
+        self.fn(name)(_p(sc[0]), _p(sc[1]), *a_in, *a_out, _p(sc[2]), _p(sc[3]), _p(sc[4]), _p(sc[5]), _p(li), _p(gi),
+                      _p(no_a), _p(rlat), _p(rlon), _p(ibo), _p(lo), _p(go), _p(iret))
+        return dict(no=int(no_a[0]), rlat=rlat, rlon=rlon, ibo=ibo, lo=lo, go=go, iret=int(iret[0]))
+
+    def ipolatev(self, ip, ipopt, gin, gout, mi, mo, km, ibi, li, ui, vi, no=0, rlat=None, rlon=None, crot=None, srot=None):
+        assert gin[0] == gout[0]
+        R = self.R
+        ui = np.ascontiguousarray(ui, dtype=R).reshape(km, mi)
+        vi = np.ascontiguousarray(vi, dtype=R).reshape(km, mi)
+        li = np.ascontiguousarray(li, dtype=np.uint8).reshape(km, mi)
+        mk = lambda a: np.zeros(mo, R) if a is None else np.ascontiguousarray(a, dtype=R).copy()
+        rlat, rlon, crot, srot = mk(rlat), mk(rlon), mk(crot), mk(srot)
+        uo = np.full((km, mo), -7777.0, R)
+        vo = np.full((km, mo), -7777.0, R)
+        lo = np.full((km, mo), 7, np.uint8)
+        ibo = self._ia([-7] * km)
+        no_a, iret = self._ia([no]), self._ia([-7])
+        a_in, keep1 = self._grid_args(gin)
+        a_out, keep2 = self._grid_args(gout)
+        sc = [self._ia([ip]), self._ia(ipopt, 20), self._ia([mi]), self._ia([mo]), self._ia([km]), self._ia(ibi, km)]
+        name = "ipolatev_grib2" if gin[0] == "grib2" else "ipolatev_grib1"
+        self.fn(name)(_p(sc[0]), _p(sc[1]), *a_in, *a_out, _p(sc[2]), _p(sc[3]), _p(sc[4]), _p(sc[5]), _p(li), _p(ui), _p(vi),
+                      _p(no_a), _p(rlat), _p(rlon), _p(crot), _p(srot), _p(ibo), _p(lo), _p(uo), _p(vo), _p(iret))
+        return dict(no=int(no_a[0]), rlat=rlat, rlon=rlon, crot=crot, srot=srot, ibo=ibo, lo=lo, uo=uo, vo=vo, iret=int(iret[0]))
+
+    def gdswzd(self, desc, iopt, npts, fill=-9999.0, xpts=None, ypts=None, rlon=None, rlat=None):
+        """The C entry (scalars by value).  Returns dict of all arrays + nret."""
+        R = self.R
+        mk = lambda a: np.zeros(npts, R) if a is None else np.ascontiguousarray(a, dtype=R).copy()
+        x, y, lon, lat = mk(xpts), mk(ypts), mk(rlon), mk(rlat)
+        ex = {k: np.full(npts, 12345.0, R) for k in ("crot", "srot", "xlon", "xlat", "ylon", "ylat", "area")}
+        nret = self._ia([-7])
+        tail = [_p(x), _p(y), _p(lon), _p(lat), _p(nret)] + [_p(ex[k]) for k in ("crot", "srot", "xlon", "xlat", "ylon", "ylat", "area")]
+        if desc[0] == "grib2":
+            t = self._ia(desc[2])
+            self.fn("gdswzd")(self.cI(desc[1]), _p(t), self.cI(t.size), self.cI(iopt), self.cI(npts), self.cR(fill), *tail)
+        else:
+            k = self._ia(desc[1], 200)
+            self.fn("gdswzd_grib1")(_p(k), self.cI(iopt), self.cI(npts), self.cR(fill), *tail)
+        return dict(xpts=x, ypts=y, rlon=lon, rlat=lat, nret=int(nret[0]), **ex)
+
+
+ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "libip_oracle.so")
+
+
+def build_oracle():
+    import subprocess
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    return ORACLE_SO
+
+
+_oracles = {}
+
+
+def oracle(kind):
+    if kind not in _oracles:
+        if not os.path.exists(ORACLE_SO):
+            build_oracle()
+        _oracles[kind] = IpLib(ORACLE_SO, "oracle_", kind)
+    return _oracles[kind]

@@ -1,0 +1,166 @@
+"""Pins the CPU oracle against the reference's own regression data.
+
+Mirrors /root/reference/tests/interp_mod_grib2.F90 / interp_mod_grib1.F90: km=1, ibi=0, default options,
+masked points set to -9 (scalar) / -9999 (vector), output cast to fp32 and compared with the golden
+record; pass criterion = the reference's (abstol 0.05 & <=10 points for _4; 1e-4 & 0 points for _d/_8).
+Additionally the _d/_8 results must be *exactly* the golden fp32 values on >= 99.99 % of points.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import ipcases as ic
+from iplib import oracle
+
+KINDS = ["4", "d", "8"]
+
+
+def _tol(kind):
+    return (0.05, 10) if kind == "4" else (1e-4, 0)
+
+
+def _grids(grib, kind, vector):
+    if grib == "grib2":
+        return ic.g2_input(kind, vector), ic.g2_templates(kind, vector)
+    return ic.g1_input(vector), ic.g1_templates()
+
+
+def check_scalar(lib, kind, grib, grid, ip):
+    gin, outs = _grids(grib, kind, False)
+    gout = outs[grid]
+    mi, mo = ic.npts_of(gin), ic.npts_of(gout)
+    r = lib.ipolates(ip, ic.ipopt_for(ip), gin, gout, mi, mo, 1, [0], np.ones(mi, np.uint8), ic.inputs()["snoalb"])
+    assert r["iret"] == 0 and r["no"] == mo
+    out = r["go"][0].copy()
+    out[r["lo"][0] == 0] = -9.0
+    out4 = out.astype(np.float32)
+    g, stride = ic.golden(grib, "4" if kind == "4" else "8", "s", grid, ip)
+    d = np.abs(out4[::stride] - g[0])
+    abstol, ntol = _tol(kind)
+    assert int((d > abstol).sum()) <= ntol, (grid, ip, int((d > abstol).sum()), float(d.max()))
+    if kind != "4":
+        assert np.mean(out4[::stride] == g[0]) >= 0.9999
+    return r
+
+
+def check_vector(lib, kind, grib, grid, ip):
+    gin, outs = _grids(grib, kind, True)
+    gout = outs[grid]
+    mi, mo = ic.npts_of(gin), ic.npts_of(gout)
+    I = ic.inputs()
+    r = lib.ipolatev(ip, ic.ipopt_for(ip), gin, gout, mi, mo, 1, [0], np.ones(mi, np.uint8), I["u"], I["v"])
+    assert r["iret"] == 0 and r["no"] == mo
+    g, stride = ic.golden(grib, "4" if kind == "4" else "8", "v", grid, ip)
+    abstol, ntol = _tol(kind)
+    nbad = 0
+    for c, nm in enumerate(("uo", "vo")):
+        out = r[nm][0].copy()
+        out[r["lo"][0] == 0] = -9999.0
+        out4 = out.astype(np.float32)
+        d = np.abs(out4[::stride] - g[c])
+        nbad += int((d > abstol).sum())
+        if kind != "4":
+            assert np.mean(out4[::stride] == g[c]) >= 0.9999
+    assert nbad <= ntol, (grid, ip, nbad)
+    return r
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("grib", ["grib2", "grib1"])
+@pytest.mark.parametrize("grid,ip", ic.SCALAR_CASES)
+def test_scalar_golden(kind, grib, grid, ip):
+    check_scalar(oracle(kind), kind, grib, grid, ip)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("grib", ["grib2", "grib1"])
+@pytest.mark.parametrize("grid,ip", ic.VECTOR_CASES)
+def test_vector_golden(kind, grib, grid, ip):
+    check_vector(oracle(kind), kind, grib, grid, ip)
+
+
+def check_station_scalar(lib, kind, grib, ip):
+    gin, _ = _grids(grib, kind, False)
+    mi = ic.npts_of(gin)
+    lat, lon = ic.STATION_SCALAR_LATLON
+    r = lib.ipolates(ip, ic.ipopt_for(ip), gin, ic.station_grid(grib), mi, 4, 1, [0], np.ones(mi, np.uint8),
+                     ic.inputs()["snoalb"], no=4, rlat=lat, rlon=lon)
+    assert not np.isnan(r["go"]).any()
+    assert np.max(np.abs(r["go"][0] - np.array(ic.STATION_SCALAR[ip]))) <= _tol(kind)[0]
+    return r
+
+
+def check_station_vector(lib, kind, grib, ip):
+    gin, _ = _grids(grib, kind, True)
+    mi = ic.npts_of(gin)
+    lat, lon = ic.STATION_VECTOR_LATLON
+    I = ic.inputs()
+    r = lib.ipolatev(ip, ic.ipopt_for(ip), gin, ic.station_grid(grib), mi, 4, 1, [0], np.ones(mi, np.uint8), I["u"], I["v"],
+                     no=4, rlat=lat, rlon=lon, crot=[1.0] * 4, srot=[0.0] * 4)
+    u, v = ic.STATION_VECTOR[ip]
+    assert not (np.isnan(r["uo"]).any() or np.isnan(r["vo"]).any())
+    assert np.max(np.abs(r["uo"][0] - np.array(u))) <= _tol(kind)[0]
+    assert np.max(np.abs(r["vo"][0] - np.array(v))) <= _tol(kind)[0]
+    return r
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("ip", [0, 1, 2, 3, 6])
+def test_station_points(kind, ip):
+    # The reference only has station known answers for the GRIB2 interface (the stations sit on
+    # half-integer rows of the input grid, so neighbour picks are rounding tie points under GRIB1's
+    # millidegree decode and are not pinned there).
+    check_station_scalar(oracle(kind), kind, "grib2", ip)
+    check_station_vector(oracle(kind), kind, "grib2", ip)
+
+
+def check_gdswzd_c(lib, grib):
+    """tests/tst_gdswzd_grib2.c, tst_gdswzd_grib1.c: rot-B 251x201, iopt=1."""
+    im, jm = 251, 201
+    if grib == "grib2":
+        desc = ("grib2", 1, [6, 255, -1, 255, -1, 255, -1, im, jm, 0, -1, -45036000, 299961000, 56, 45036000, 60039000, 0, 0, 64,
+                            -36000000, 254000000, 0])
+    else:
+        desc = ("grib1", [205, im, jm, -7446, -144139, 8, 54000, -106000, 0, 0, 64, 44560, 14744] + [0] * 187)
+    x = np.tile(np.arange(1, im + 1), jm)
+    y = np.repeat(np.arange(1, jm + 1), im)
+    r = lib.gdswzd(desc, 1, im * jm, -9999.0, xpts=x, ypts=y)
+    assert r["nret"] == 50451
+    assert abs(r["rlat"][0] - (-7.491)) / 7.491 < 0.01 and abs(r["rlon"][0] - 360.0 - (-144.134)) / 144.134 < 0.01
+    assert abs(r["rlat"][-1] - 44.539) / 44.539 < 0.01 and abs(r["rlon"][-1] - 14.802) / 14.802 < 0.01
+    return r
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("grib", ["grib2", "grib1"])
+def test_gdswzd_c_entry(kind, grib):
+    r = check_gdswzd_c(oracle(kind), grib)
+    # every optional output is filled for valid points
+    for k in ("crot", "srot", "xlon", "xlat", "ylon", "ylat", "area"):
+        assert np.isfinite(r[k]).all() and not (r[k] == 12345.0).any()
+    assert np.allclose(r["crot"] ** 2 + r["srot"] ** 2, 1.0, atol=1e-5)
+    assert (r["area"] > 0).all()
+
+
+def test_earth_radius():
+    """tests/test_earth_radius.F90 (exact to epsilon)."""
+    lib = oracle("4").lib
+    for sfx, ct, eps in (("4", C.c_float, np.finfo(np.float32).eps), ("d", C.c_double, np.finfo(np.float64).eps)):
+        f = getattr(lib, "oracle_earth_radius_" + sfx)
+
+        def er(t):
+            a = np.array(t + [0] * (7 - len(t)), np.int32)
+            r, e = ct(), ct()
+            f(a.ctypes.data_as(C.c_void_p), C.c_int32(7), C.byref(r), C.byref(e))
+            return r.value, e.value
+
+        cases = [([0], 6367470.0, 0.0), ([1, 1, 1], 0.1, 0.0), ([1, 2, 63600000], 636000.0, 0.0),
+                 ([2], 6378160.0, 6.7226700223333219e-3), ([3, 0, 0, 1, 1, 1, 1], 100.0, 0.0),
+                 ([4], 6378137.0, 6.6943805181245335e-3), ([5], 6378137.0, 6.69437999013e-3), ([6], 6371229.0, 0.0),
+                 ([7, 0, 0, 1, 1, 1, 1], 0.1, 0.0), ([8], 6371200.0, 0.0), ([9], -9999.0, -9999.0)]
+        for t, rad, e2 in cases:
+            r, e = er(t)
+            # the reference's literals are default-kind reals: compare at the kind's own rounding
+            assert abs(r - (np.float32(rad) if sfx == "4" else rad)) <= eps * max(1.0, abs(rad)), (t, r)
+            assert abs(e - (np.float32(e2) if sfx == "4" else e2)) <= eps * 4, (t, e)
