@@ -1,8 +1,13 @@
-"""ctypes front end shared by the oracle and the product library.
+"""Python mirror of the reference's `ip_mod` facade (src/ip_mod.F90:7-20) over the C ABI.
 
-Both export the reference's bind(c) argument lists (src/ipolates.F90:587-636 etc.); only the
-symbol prefix differs ("oracle_" for oracle/_build/libip_oracle.so, "" for the product's
-libipb200.so), and every symbol carries the build-kind suffix _4 / _d / _8.
+`IpLib` binds a shared library that exports the reference's bind(c) argument lists
+(src/ipolates.F90:158,293,587,808; src/ipolatev.F90:382,565,680,832; src/gdswzd_c.F90:173,259)
+with the build-kind suffix _4 / _d / _8 on every symbol.  `load(kind)` returns the binder for the
+product library (libipb200.so, CUDA); there is no CPU path — a missing library or device is an
+error.  The tests bind the CPU oracle through the same class with prefix "oracle_".
+
+Arrays follow the Fortran layout seen from C: field k of gi starts at k*mi, so a numpy array of
+shape [km, mi] in C order is GI(MI,KM).
 """
 import ctypes as C
 import os
@@ -11,6 +16,9 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
+
+BILINEAR_INTERP_ID, BICUBIC_INTERP_ID, NEIGHBOR_INTERP_ID, BUDGET_INTERP_ID = 0, 1, 2, 3
+SPECTRAL_INTERP_ID, NEIGHBOR_BUDGET_INTERP_ID = 4, 6  # src/ip_interpolators_mod.F90:17-27
 
 KINDS = {"4": (np.float32, np.int32), "d": (np.float64, np.int32), "8": (np.float64, np.int64)}
 
@@ -105,21 +113,16 @@ class IpLib:
         return dict(xpts=x, ypts=y, rlon=lon, rlat=lat, nret=int(nret[0]), **ex)
 
 
-ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "libip_oracle.so")
+PRODUCT_SO = os.path.join(HERE, "libipb200.so")
+
+_libs = {}
 
 
-def build_oracle():
-    import subprocess
-    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
-    return ORACLE_SO
-
-
-_oracles = {}
-
-
-def oracle(kind):
-    if kind not in _oracles:
-        if not os.path.exists(ORACLE_SO):
-            build_oracle()
-        _oracles[kind] = IpLib(ORACLE_SO, "oracle_", kind)
-    return _oracles[kind]
+def load(kind="4"):
+    """Binder for the CUDA library in build kind '4', 'd' or '8'."""
+    if kind not in _libs:
+        if not os.path.exists(PRODUCT_SO):
+            raise RuntimeError(f"{PRODUCT_SO} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)")
+        _libs[kind] = IpLib(PRODUCT_SO, "", kind)
+    return _libs[kind]
