@@ -1,0 +1,241 @@
+/* ipb200.h — C ABI of the B200-native ipolates / ipolatev / gdswzd library (libipb200.so).
+ *
+ * Drop-in boundary for the hot path of NOAA-EMC/NCEPLIBS-ip 5.0.0.  Every interpolation entry point
+ * below has exactly the argument list of the reference's own bind(c) driver (all arguments by
+ * reference, arrays contiguous in Fortran column-major order, LOGICAL(C_BOOL) = one byte); the two
+ * gdswzd entry points have the argument lists of the reference's C wrappers (scalars by value).
+ * The reference builds three libraries from one source (src/CMakeLists.txt:36-76); here the build
+ * kind is a symbol suffix instead:
+ *     _4  INTEGER(4)/REAL(4)  (libip_4)     _d  INTEGER(4)/REAL(8)  (libip_d)     _8  INTEGER(8)/REAL(8)  (libip_8)
+ *
+ * Array shapes (Fortran):  ipopt(20), kgds*(200), igdtmpl*(igdtlen*), ibi(km), li(mi,km), gi/ui/vi(mi,km),
+ * rlat/rlon/crot/srot(mo), ibo(km), lo(mo,km), go/uo/vo(mo,km).  Field k (0-based) of gi starts at gi + k*mi.
+ * In/out conventions, iret codes (0 ok, 2 no overlap, 3 bad output grid / mo too small, 32 bad ipopt) and
+ * the option words are the reference's (docs in src/ipolates.F90:337-586, src/ipolatev.F90:122-381).
+ * Additional codes produced only by this library: iret = 1 for a grid template or method it does not
+ * implement (the reference error-stops), iret = 1000 + cudaError for a CUDA failure.
+ * ip = 4 (spectral) is out of scope.  There is no CPU fallback: without a CUDA device the library aborts.
+ *
+ * The *_single_field entry points take scalar ibi / ibo and rank-1 li, gi, lo, go; km is ignored (1).
+ */
+#ifndef IPB200_H
+#define IPB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef unsigned char ipb_bool; /* LOGICAL(C_BOOL) / LOGICAL*1 */
+
+/* ======================== kind _4  (libip_4: default INTEGER(4), REAL(4)) ======================== */
+/* replaces ipolates_grib2, src/ipolates.F90:587-636 */
+void ipolates_grib2_4(
+    const int32_t* ip, const int32_t* ipopt, const int32_t* igdtnumi, const int32_t* igdtmpli, const int32_t* igdtleni, const int32_t* igdtnumo, const int32_t* igdtmplo, const int32_t* igdtleno,
+    const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const float* gi,
+    int32_t* no, float* rlat, float* rlon, int32_t* ibo, ipb_bool* lo, float* go, int32_t* iret);
+/* replaces ipolates_grib2_single_field, src/ipolates.F90:808-864 */
+void ipolates_grib2_single_field_4(
+    const int32_t* ip, const int32_t* ipopt, const int32_t* igdtnumi, const int32_t* igdtmpli, const int32_t* igdtleni, const int32_t* igdtnumo, const int32_t* igdtmplo, const int32_t* igdtleno,
+    const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const float* gi,
+    int32_t* no, float* rlat, float* rlon, int32_t* ibo, ipb_bool* lo, float* go, int32_t* iret);
+/* replaces ipolates_grib1, src/ipolates.F90:293-334 */
+void ipolates_grib1_4(
+    const int32_t* ip, const int32_t* ipopt, const int32_t* kgdsi, const int32_t* kgdso,
+    const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const float* gi,
+    int32_t* no, float* rlat, float* rlon, int32_t* ibo, ipb_bool* lo, float* go, int32_t* iret);
+/* replaces ipolates_grib1_single_field, src/ipolates.F90:158-206 */
+void ipolates_grib1_single_field_4(
+    const int32_t* ip, const int32_t* ipopt, const int32_t* kgdsi, const int32_t* kgdso,
+    const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const float* gi,
+    int32_t* no, float* rlat, float* rlon, int32_t* ibo, ipb_bool* lo, float* go, int32_t* iret);
+/* replaces ipolatev_grib2, src/ipolatev.F90:382-434 */
+void ipolatev_grib2_4(
+    const int32_t* ip, const int32_t* ipopt, const int32_t* igdtnumi, const int32_t* igdtmpli, const int32_t* igdtleni, const int32_t* igdtnumo, const int32_t* igdtmplo, const int32_t* igdtleno,
+    const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const float* ui, const float* vi,
+    int32_t* no, float* rlat, float* rlon, float* crot, float* srot, int32_t* ibo, ipb_bool* lo, float* uo, float* vo, int32_t* iret);
+/* replaces ipolatev_grib2_single_field, src/ipolatev.F90:832-891 */
+void ipolatev_grib2_single_field_4(
+    const int32_t* ip, const int32_t* ipopt, const int32_t* igdtnumi, const int32_t* igdtmpli, const int32_t* igdtleni, const int32_t* igdtnumo, const int32_t* igdtmplo, const int32_t* igdtleno,
+    const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const float* ui, const float* vi,
+    int32_t* no, float* rlat, float* rlon, float* crot, float* srot, int32_t* ibo, ipb_bool* lo, float* uo, float* vo, int32_t* iret);
+/* replaces ipolatev_grib1, src/ipolatev.F90:565-628 (the 203 -> wind-point switch of kgds(11) is applied internally; the caller's kgds is not modified) */
+void ipolatev_grib1_4(
+    const int32_t* ip, const int32_t* ipopt, const int32_t* kgdsi, const int32_t* kgdso,
+    const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const float* ui, const float* vi,
+    int32_t* no, float* rlat, float* rlon, float* crot, float* srot, int32_t* ibo, ipb_bool* lo, float* uo, float* vo, int32_t* iret);
+/* replaces ipolatev_grib1_single_field, src/ipolatev.F90:680-750 */
+void ipolatev_grib1_single_field_4(
+    const int32_t* ip, const int32_t* ipopt, const int32_t* kgdsi, const int32_t* kgdso,
+    const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const float* ui, const float* vi,
+    int32_t* no, float* rlat, float* rlon, float* crot, float* srot, int32_t* ibo, ipb_bool* lo, float* uo, float* vo, int32_t* iret);
+/* replaces the C symbol gdswzd, src/gdswzd_c.F90:173-210 (prototype src/iplib_4.h:146); optional outputs may be NULL */
+void gdswzd_4(
+    int32_t igdtnum, const int32_t* igdtmpl, int32_t igdtlen, int32_t iopt, int32_t npts, float fill,
+    float* xpts, float* ypts, float* rlon, float* rlat, int32_t* nret,
+    float* crot, float* srot, float* xlon, float* xlat, float* ylon, float* ylat, float* area);
+/* replaces the C symbol gdswzd_grib1, src/gdswzd_c.F90:259-292 (prototype src/iplib_4.h:187) */
+void gdswzd_grib1_4(
+    const int32_t* kgds, int32_t iopt, int32_t npts, float fill,
+    float* xpts, float* ypts, float* rlon, float* rlat, int32_t* nret,
+    float* crot, float* srot, float* xlon, float* xlat, float* ylon, float* ylat, float* area);
+/* Device-resident variants (new): li, gi/ui/vi, lo, go/uo/vo are DEVICE pointers and so are
+ * rlat, rlon, crot, srot (each may be NULL to skip that output; for station-point outputs they are inputs).
+ * Scalars, ipopt, the grid definition, ibi, ibo, no and iret stay host memory.  Work is queued on `stream`
+ * (a cudaStream_t) and the call returns after that stream has drained. */
+void ipgpu_ipolates_grib2_dev_4(
+    void* stream, const int32_t* ip, const int32_t* ipopt, const int32_t* igdtnumi, const int32_t* igdtmpli, const int32_t* igdtleni, const int32_t* igdtnumo, const int32_t* igdtmplo, const int32_t* igdtleno,
+    const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const float* gi,
+    int32_t* no, float* rlat, float* rlon, int32_t* ibo, ipb_bool* lo, float* go, int32_t* iret);
+void ipgpu_ipolatev_grib2_dev_4(
+    void* stream, const int32_t* ip, const int32_t* ipopt, const int32_t* igdtnumi, const int32_t* igdtmpli, const int32_t* igdtleni, const int32_t* igdtnumo, const int32_t* igdtmplo, const int32_t* igdtleno,
+    const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const float* ui, const float* vi,
+    int32_t* no, float* rlat, float* rlon, float* crot, float* srot, int32_t* ibo, ipb_bool* lo, float* uo, float* vo, int32_t* iret);
+
+/* ======================== kind _d  (libip_d: INTEGER(4), REAL(8)) ======================== */
+/* replaces ipolates_grib2, src/ipolates.F90:587-636 */
+void ipolates_grib2_d(
+    const int32_t* ip, const int32_t* ipopt, const int32_t* igdtnumi, const int32_t* igdtmpli, const int32_t* igdtleni, const int32_t* igdtnumo, const int32_t* igdtmplo, const int32_t* igdtleno,
+    const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const double* gi,
+    int32_t* no, double* rlat, double* rlon, int32_t* ibo, ipb_bool* lo, double* go, int32_t* iret);
+/* replaces ipolates_grib2_single_field, src/ipolates.F90:808-864 */
+void ipolates_grib2_single_field_d(
+    const int32_t* ip, const int32_t* ipopt, const int32_t* igdtnumi, const int32_t* igdtmpli, const int32_t* igdtleni, const int32_t* igdtnumo, const int32_t* igdtmplo, const int32_t* igdtleno,
+    const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const double* gi,
+    int32_t* no, double* rlat, double* rlon, int32_t* ibo, ipb_bool* lo, double* go, int32_t* iret);
+/* replaces ipolates_grib1, src/ipolates.F90:293-334 */
+void ipolates_grib1_d(
+    const int32_t* ip, const int32_t* ipopt, const int32_t* kgdsi, const int32_t* kgdso,
+    const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const double* gi,
+    int32_t* no, double* rlat, double* rlon, int32_t* ibo, ipb_bool* lo, double* go, int32_t* iret);
+/* replaces ipolates_grib1_single_field, src/ipolates.F90:158-206 */
+void ipolates_grib1_single_field_d(
+    const int32_t* ip, const int32_t* ipopt, const int32_t* kgdsi, const int32_t* kgdso,
+    const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const double* gi,
+    int32_t* no, double* rlat, double* rlon, int32_t* ibo, ipb_bool* lo, double* go, int32_t* iret);
+/* replaces ipolatev_grib2, src/ipolatev.F90:382-434 */
+void ipolatev_grib2_d(
+    const int32_t* ip, const int32_t* ipopt, const int32_t* igdtnumi, const int32_t* igdtmpli, const int32_t* igdtleni, const int32_t* igdtnumo, const int32_t* igdtmplo, const int32_t* igdtleno,
+    const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const double* ui, const double* vi,
+    int32_t* no, double* rlat, double* rlon, double* crot, double* srot, int32_t* ibo, ipb_bool* lo, double* uo, double* vo, int32_t* iret);
+/* replaces ipolatev_grib2_single_field, src/ipolatev.F90:832-891 */
+void ipolatev_grib2_single_field_d(
+    const int32_t* ip, const int32_t* ipopt, const int32_t* igdtnumi, const int32_t* igdtmpli, const int32_t* igdtleni, const int32_t* igdtnumo, const int32_t* igdtmplo, const int32_t* igdtleno,
+    const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const double* ui, const double* vi,
+    int32_t* no, double* rlat, double* rlon, double* crot, double* srot, int32_t* ibo, ipb_bool* lo, double* uo, double* vo, int32_t* iret);
+/* replaces ipolatev_grib1, src/ipolatev.F90:565-628 (the 203 -> wind-point switch of kgds(11) is applied internally; the caller's kgds is not modified) */
+void ipolatev_grib1_d(
+    const int32_t* ip, const int32_t* ipopt, const int32_t* kgdsi, const int32_t* kgdso,
+    const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const double* ui, const double* vi,
+    int32_t* no, double* rlat, double* rlon, double* crot, double* srot, int32_t* ibo, ipb_bool* lo, double* uo, double* vo, int32_t* iret);
+/* replaces ipolatev_grib1_single_field, src/ipolatev.F90:680-750 */
+void ipolatev_grib1_single_field_d(
+    const int32_t* ip, const int32_t* ipopt, const int32_t* kgdsi, const int32_t* kgdso,
+    const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const double* ui, const double* vi,
+    int32_t* no, double* rlat, double* rlon, double* crot, double* srot, int32_t* ibo, ipb_bool* lo, double* uo, double* vo, int32_t* iret);
+/* replaces the C symbol gdswzd, src/gdswzd_c.F90:173-210 (prototype src/iplib_d.h:146); optional outputs may be NULL */
+void gdswzd_d(
+    int32_t igdtnum, const int32_t* igdtmpl, int32_t igdtlen, int32_t iopt, int32_t npts, double fill,
+    double* xpts, double* ypts, double* rlon, double* rlat, int32_t* nret,
+    double* crot, double* srot, double* xlon, double* xlat, double* ylon, double* ylat, double* area);
+/* replaces the C symbol gdswzd_grib1, src/gdswzd_c.F90:259-292 (prototype src/iplib_d.h:187) */
+void gdswzd_grib1_d(
+    const int32_t* kgds, int32_t iopt, int32_t npts, double fill,
+    double* xpts, double* ypts, double* rlon, double* rlat, int32_t* nret,
+    double* crot, double* srot, double* xlon, double* xlat, double* ylon, double* ylat, double* area);
+/* Device-resident variants (new): li, gi/ui/vi, lo, go/uo/vo are DEVICE pointers and so are
+ * rlat, rlon, crot, srot (each may be NULL to skip that output; for station-point outputs they are inputs).
+ * Scalars, ipopt, the grid definition, ibi, ibo, no and iret stay host memory.  Work is queued on `stream`
+ * (a cudaStream_t) and the call returns after that stream has drained. */
+void ipgpu_ipolates_grib2_dev_d(
+    void* stream, const int32_t* ip, const int32_t* ipopt, const int32_t* igdtnumi, const int32_t* igdtmpli, const int32_t* igdtleni, const int32_t* igdtnumo, const int32_t* igdtmplo, const int32_t* igdtleno,
+    const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const double* gi,
+    int32_t* no, double* rlat, double* rlon, int32_t* ibo, ipb_bool* lo, double* go, int32_t* iret);
+void ipgpu_ipolatev_grib2_dev_d(
+    void* stream, const int32_t* ip, const int32_t* ipopt, const int32_t* igdtnumi, const int32_t* igdtmpli, const int32_t* igdtleni, const int32_t* igdtnumo, const int32_t* igdtmplo, const int32_t* igdtleno,
+    const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const double* ui, const double* vi,
+    int32_t* no, double* rlat, double* rlon, double* crot, double* srot, int32_t* ibo, ipb_bool* lo, double* uo, double* vo, int32_t* iret);
+
+/* ======================== kind _8  (libip_8: INTEGER(8), REAL(8)) ======================== */
+/* replaces ipolates_grib2, src/ipolates.F90:587-636 */
+void ipolates_grib2_8(
+    const int64_t* ip, const int64_t* ipopt, const int64_t* igdtnumi, const int64_t* igdtmpli, const int64_t* igdtleni, const int64_t* igdtnumo, const int64_t* igdtmplo, const int64_t* igdtleno,
+    const int64_t* mi, const int64_t* mo, const int64_t* km, const int64_t* ibi, const ipb_bool* li, const double* gi,
+    int64_t* no, double* rlat, double* rlon, int64_t* ibo, ipb_bool* lo, double* go, int64_t* iret);
+/* replaces ipolates_grib2_single_field, src/ipolates.F90:808-864 */
+void ipolates_grib2_single_field_8(
+    const int64_t* ip, const int64_t* ipopt, const int64_t* igdtnumi, const int64_t* igdtmpli, const int64_t* igdtleni, const int64_t* igdtnumo, const int64_t* igdtmplo, const int64_t* igdtleno,
+    const int64_t* mi, const int64_t* mo, const int64_t* km, const int64_t* ibi, const ipb_bool* li, const double* gi,
+    int64_t* no, double* rlat, double* rlon, int64_t* ibo, ipb_bool* lo, double* go, int64_t* iret);
+/* replaces ipolates_grib1, src/ipolates.F90:293-334 */
+void ipolates_grib1_8(
+    const int64_t* ip, const int64_t* ipopt, const int64_t* kgdsi, const int64_t* kgdso,
+    const int64_t* mi, const int64_t* mo, const int64_t* km, const int64_t* ibi, const ipb_bool* li, const double* gi,
+    int64_t* no, double* rlat, double* rlon, int64_t* ibo, ipb_bool* lo, double* go, int64_t* iret);
+/* replaces ipolates_grib1_single_field, src/ipolates.F90:158-206 */
+void ipolates_grib1_single_field_8(
+    const int64_t* ip, const int64_t* ipopt, const int64_t* kgdsi, const int64_t* kgdso,
+    const int64_t* mi, const int64_t* mo, const int64_t* km, const int64_t* ibi, const ipb_bool* li, const double* gi,
+    int64_t* no, double* rlat, double* rlon, int64_t* ibo, ipb_bool* lo, double* go, int64_t* iret);
+/* replaces ipolatev_grib2, src/ipolatev.F90:382-434 */
+void ipolatev_grib2_8(
+    const int64_t* ip, const int64_t* ipopt, const int64_t* igdtnumi, const int64_t* igdtmpli, const int64_t* igdtleni, const int64_t* igdtnumo, const int64_t* igdtmplo, const int64_t* igdtleno,
+    const int64_t* mi, const int64_t* mo, const int64_t* km, const int64_t* ibi, const ipb_bool* li, const double* ui, const double* vi,
+    int64_t* no, double* rlat, double* rlon, double* crot, double* srot, int64_t* ibo, ipb_bool* lo, double* uo, double* vo, int64_t* iret);
+/* replaces ipolatev_grib2_single_field, src/ipolatev.F90:832-891 */
+void ipolatev_grib2_single_field_8(
+    const int64_t* ip, const int64_t* ipopt, const int64_t* igdtnumi, const int64_t* igdtmpli, const int64_t* igdtleni, const int64_t* igdtnumo, const int64_t* igdtmplo, const int64_t* igdtleno,
+    const int64_t* mi, const int64_t* mo, const int64_t* km, const int64_t* ibi, const ipb_bool* li, const double* ui, const double* vi,
+    int64_t* no, double* rlat, double* rlon, double* crot, double* srot, int64_t* ibo, ipb_bool* lo, double* uo, double* vo, int64_t* iret);
+/* replaces ipolatev_grib1, src/ipolatev.F90:565-628 (the 203 -> wind-point switch of kgds(11) is applied internally; the caller's kgds is not modified) */
+void ipolatev_grib1_8(
+    const int64_t* ip, const int64_t* ipopt, const int64_t* kgdsi, const int64_t* kgdso,
+    const int64_t* mi, const int64_t* mo, const int64_t* km, const int64_t* ibi, const ipb_bool* li, const double* ui, const double* vi,
+    int64_t* no, double* rlat, double* rlon, double* crot, double* srot, int64_t* ibo, ipb_bool* lo, double* uo, double* vo, int64_t* iret);
+/* replaces ipolatev_grib1_single_field, src/ipolatev.F90:680-750 */
+void ipolatev_grib1_single_field_8(
+    const int64_t* ip, const int64_t* ipopt, const int64_t* kgdsi, const int64_t* kgdso,
+    const int64_t* mi, const int64_t* mo, const int64_t* km, const int64_t* ibi, const ipb_bool* li, const double* ui, const double* vi,
+    int64_t* no, double* rlat, double* rlon, double* crot, double* srot, int64_t* ibo, ipb_bool* lo, double* uo, double* vo, int64_t* iret);
+/* replaces the C symbol gdswzd, src/gdswzd_c.F90:173-210 (prototype src/iplib_8.h:146); optional outputs may be NULL */
+void gdswzd_8(
+    int64_t igdtnum, const int64_t* igdtmpl, int64_t igdtlen, int64_t iopt, int64_t npts, double fill,
+    double* xpts, double* ypts, double* rlon, double* rlat, int64_t* nret,
+    double* crot, double* srot, double* xlon, double* xlat, double* ylon, double* ylat, double* area);
+/* replaces the C symbol gdswzd_grib1, src/gdswzd_c.F90:259-292 (prototype src/iplib_8.h:187) */
+void gdswzd_grib1_8(
+    const int64_t* kgds, int64_t iopt, int64_t npts, double fill,
+    double* xpts, double* ypts, double* rlon, double* rlat, int64_t* nret,
+    double* crot, double* srot, double* xlon, double* xlat, double* ylon, double* ylat, double* area);
+/* Device-resident variants (new): li, gi/ui/vi, lo, go/uo/vo are DEVICE pointers and so are
+ * rlat, rlon, crot, srot (each may be NULL to skip that output; for station-point outputs they are inputs).
+ * Scalars, ipopt, the grid definition, ibi, ibo, no and iret stay host memory.  Work is queued on `stream`
+ * (a cudaStream_t) and the call returns after that stream has drained. */
+void ipgpu_ipolates_grib2_dev_8(
+    void* stream, const int64_t* ip, const int64_t* ipopt, const int64_t* igdtnumi, const int64_t* igdtmpli, const int64_t* igdtleni, const int64_t* igdtnumo, const int64_t* igdtmplo, const int64_t* igdtleno,
+    const int64_t* mi, const int64_t* mo, const int64_t* km, const int64_t* ibi, const ipb_bool* li, const double* gi,
+    int64_t* no, double* rlat, double* rlon, int64_t* ibo, ipb_bool* lo, double* go, int64_t* iret);
+void ipgpu_ipolatev_grib2_dev_8(
+    void* stream, const int64_t* ip, const int64_t* ipopt, const int64_t* igdtnumi, const int64_t* igdtmpli, const int64_t* igdtleni, const int64_t* igdtnumo, const int64_t* igdtmplo, const int64_t* igdtleno,
+    const int64_t* mi, const int64_t* mo, const int64_t* km, const int64_t* ibi, const ipb_bool* li, const double* ui, const double* vi,
+    int64_t* no, double* rlat, double* rlon, double* crot, double* srot, int64_t* ibo, ipb_bool* lo, double* uo, double* vo, int64_t* iret);
+
+/* ======================== library management (new; no reference counterpart) ======================== */
+int ipgpu_device_count(void);                     /* CUDA devices visible to the process */
+int ipgpu_set_device(int device);                 /* cudaSetDevice; call before the first interpolation (one process per GPU) */
+void ipgpu_plan_clear(void);                      /* drop every cached plan and the staging buffers */
+long long ipgpu_plan_count(void);                 /* plans resident in HBM */
+long long ipgpu_plan_bytes(void);                 /* bytes they hold */
+void ipgpu_set_plan_cache_bytes(long long bytes); /* LRU capacity of the plan cache (default 24 GiB) */
+void ipgpu_set_chunk_bytes(long long bytes);      /* staging size per in-flight chunk of the host-pointer API (default 768 MiB) */
+long long ipgpu_launch_count(void);               /* kernels launched by this library since load */
+void ipgpu_last_timing(double* plan_ms, double* apply_ms, int* plan_cache_hit); /* CUDA-event times of the last call */
+void ipgpu_last_transfer(long long* h2d_bytes, long long* d2h_bytes); /* field bytes the last host-pointer call moved over PCIe */
+void* ipgpu_host_alloc(long long bytes);          /* pinned host memory (cudaMallocHost) so the host API copies asynchronously */
+void ipgpu_host_free(void* p);
+const char* ipgpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPB200_H */

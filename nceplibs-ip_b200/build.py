@@ -1,17 +1,23 @@
-"""Builds libipb200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+"""Builds libipb200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+Three translation units (the C ABI and one instantiation of the kernels per real kind) are compiled
+in parallel and linked into one shared library next to this file.
+"""
 import os
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
 OUT = os.path.join(HERE, "libipb200.so")
+UNITS = ["ipb_api.cu", "ipb_kind_f32.cu", "ipb_kind_f64.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",           # the reference is built without FMA contraction; rounding is part of the contract
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-fast-math", "-Xcompiler", "-ffp-contract=off",
     "-Xcudafe", "--diag_suppress=177",
-    "-shared",
 ]
 
 
@@ -26,12 +32,28 @@ def up_to_date():
     return all(os.path.getmtime(s) <= t for s in sources())
 
 
-def build_library(force=False, verbose=False):
+def build_library(force=False, verbose=False, extra=()):
     if not force and up_to_date():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", OUT, os.path.join(CSRC, "ipb_api.cu")]
+    os.makedirs(OBJ, exist_ok=True)
+
+    def compile_one(u):
+        o = os.path.join(OBJ, u.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + list(extra) + ["-c", "-o", o, os.path.join(CSRC, u)]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0 or (verbose and r.stderr.strip()):
+            print(r.stdout + r.stderr, flush=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {u}")
+        return o
+
+    with ThreadPoolExecutor(len(UNITS)) as ex:
+        objs = list(ex.map(compile_one, UNITS))
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + objs
     if verbose:
-        print(" ".join(cmd))
+        print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)
     return OUT

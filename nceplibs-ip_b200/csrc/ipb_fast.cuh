@@ -1,8 +1,171 @@
-// ipb200 — vectorised bilinear apply path (placeholder until the first parity run is green).
+// ipb200 — the streaming bilinear apply kernel (ipolates ip=0, the BASELINE headline path).
+//
+// What the reference does per (output point, field) — src/bilinear_interp_mod.F90:202-261 — is a
+// 4-tap masked weighted sum followed by a divide and a 5-byte store (go + lo).  At the headline
+// configuration the output grid oversamples the source ~66x, so the loop is a *write-bound
+// stream*: 5.09 algorithmic bytes per point-field, of which 5 are stores.
+// This kernel is built around that:
+//
+//  * a thread owns FOUR consecutive output points and walks a slice of the field batch with the
+//    16 tap offsets / weights, the per-point weight sums, their reciprocals and the packed lo
+//    word held in registers: the plan is read once per slice, not once per field;
+//  * go is stored as one 16-byte (fp32) / 32-byte (fp64) vector and lo as one 32-bit word per
+//    thread and field, with streaming (evict-first) hints so the 10 GB output stream does not
+//    push the plan and the touched source window out of L2;
+//  * field k of go starts at element k*mo, which is only vector-aligned for some k.  Fields are
+//    therefore split into four alignment classes (k mod 4); a block works on one class, and the
+//    thread->point mapping is shifted per class so every vector store is aligned;
+//  * when no bitmap is in play the weight sum W and lo do not depend on the field, and G/W is
+//    formed as a correctly rounded quotient from the stored correctly rounded reciprocal
+//    (two fused residual corrections, Markstein) instead of a full IEEE division sequence;
+//  * blockIdx.x runs over field slices, blockIdx.y over point blocks, so blocks that are
+//    resident together share the same plan segment (L2 hits) while streaming different fields.
+//
+// Accumulation order and every rounding are the reference's: taps (1,1),(2,1),(1,2),(2,2), one
+// multiply and one add each (the library is compiled with -fmad=false).
 #pragma once
 #include "ipb_apply.cuh"
 
 namespace ipb {
-template <class R> bool fast_bilinear_ok(const Plan<R>&, const FieldArgs<R>&) { return false; }
-template <class R> void launch_fast_bilinear(const Plan<R>&, const FieldArgs<R>&, cudaStream_t) {}
+
+template <class R> __device__ __forceinline__ R fma_r(R a, R b, R c);
+template <> __device__ __forceinline__ float fma_r<float>(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+template <> __device__ __forceinline__ double fma_r<double>(double a, double b, double c) { return __fma_rn(a, b, c); }
+
+// g / w, correctly rounded, given rw = RN(1/w).  q0 = RN(g*rw) is within 2 ulp; one fused residual
+// step makes it faithful and the second one correctly rounded (Markstein's theorem needs rw
+// correctly rounded and a faithful q).  Outside the exponent window where the residuals are exact
+// the plain division is used.
+template <class R> __device__ __forceinline__ R quot(R g, R w, R rw) {
+  const R ag = g < 0 ? -g : g;
+  const R lo = sizeof(R) == 4 ? (R)1e-25f : (R)1e-250, hi = sizeof(R) == 4 ? (R)1e25f : (R)1e250;
+  if (!(ag < hi) || (ag < lo && ag != 0)) return g / w;
+  R q = g * rw;
+  R r = fma_r<R>(-q, w, g);
+  q = fma_r<R>(r, rw, q);
+  r = fma_r<R>(-q, w, g);
+  return fma_r<R>(r, rw, q);
+}
+
+template <class R> __device__ __forceinline__ void store4(R* p, R a, R b, R c, R d);
+template <> __device__ __forceinline__ void store4<float>(float* p, float a, float b, float c, float d) {
+  __stcs(reinterpret_cast<float4*>(p), make_float4(a, b, c, d));
+}
+template <> __device__ __forceinline__ void store4<double>(double* p, double a, double b, double c, double d) {
+  __stcs(reinterpret_cast<double2*>(p), make_double2(a, b));
+  __stcs(reinterpret_cast<double2*>(p) + 1, make_double2(c, d));
+}
+
+// One output point, one field, any mask state: the reference loop body without the spiral search.
+template <class R>
+__device__ __forceinline__ bool bilinear_point(const R* __restrict__ g, const u8* __restrict__ l, bool masked, const int (&idx)[4],
+                                               const R (&w)[4], R pmp, R& out) {
+  R G = 0, W = 0;
+#pragma unroll
+  for (int t = 0; t < 4; t++) {
+    const int p = idx[t];
+    if (p > 0 && (!masked || l[p - 1])) {
+      G = G + w[t] * __ldg(g + (p - 1));
+      W = W + w[t];
+    }
+  }
+  const bool good = W >= pmp;
+  out = good ? G / W : (R)0;
+  return good;
+}
+
+// KPT = fields walked by one thread.  blockIdx.x = 4*slice + class, blockIdx.y = point block.
+template <class R, int KPT>
+__global__ void __launch_bounds__(128)
+k_bilinear_stream(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restrict__ wxy, int base_mis) {
+  const int cls = blockIdx.x & 3, slice = blockIdx.x >> 2;
+  // first output point whose element offset is a multiple of 4 for fields of this class
+  const int first = (4 - (int)(((long long)base_mis + (long long)cls * a.mo) & 3)) & 3;
+  const int n0 = (first ? first - 4 : 0) + 4 * (int)(blockIdx.y * blockDim.x + threadIdx.x);
+  if (n0 >= a.no) return;
+  int idx[4][4];
+  R w[4][4], W[4], rW[4];
+  bool full = true;        // all four points inside, every tap present, every point passes the mask threshold
+  unsigned goodbits = 0;   // bit p: point p passes when no bitmap is involved
+#pragma unroll
+  for (int p = 0; p < 4; p++) {
+    const int n = n0 + p;
+    const bool in = n >= 0 && n < a.no;
+    R ws = 0;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      idx[p][t] = in ? nxy[(size_t)t * a.no + n] : 0;
+      w[p][t] = in ? wxy[(size_t)t * a.no + n] : (R)0;
+      if (idx[p][t] > 0) ws = ws + w[p][t]; else full = false;
+    }
+    W[p] = ws;
+    rW[p] = (R)1 / ws;
+    const bool good = in && ws >= a.pmp;
+    if (good) goodbits |= 1u << p;
+    full = full && good;
+  }
+  const unsigned lo_word = (goodbits & 1u) | ((goodbits & 2u) << 7) | ((goodbits & 4u) << 14) | ((goodbits & 8u) << 21);
+  const bool all_in = n0 >= 0 && n0 + 3 < a.no;
+  const int kbeg = cls + 4 * slice * KPT;
+#pragma unroll 1
+  for (int j = 0; j < KPT; j++) {
+    const int k = kbeg + 4 * j;
+    if (k >= a.kc) break;
+    const R* __restrict__ g = a.gi + (size_t)k * a.mi;
+    const size_t ob = (size_t)k * a.mo;
+    const bool masked = a.ibi[k] != 0;
+    if (!masked && full) {
+      R o[4];
+#pragma unroll
+      for (int p = 0; p < 4; p++) {
+        R G = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) G = G + w[p][t] * __ldg(g + (idx[p][t] - 1));
+        o[p] = quot<R>(G, W[p], rW[p]);
+      }
+      store4<R>(a.go + ob + n0, o[0], o[1], o[2], o[3]);
+      __stcs(reinterpret_cast<unsigned*>(a.lo + ob + n0), lo_word);
+    } else {
+      const u8* __restrict__ l = a.li ? a.li + (size_t)k * a.mi : nullptr;
+      R o[4];
+      unsigned lw = 0;
+      bool bad = false;
+#pragma unroll
+      for (int p = 0; p < 4; p++) {
+        const bool good = bilinear_point<R>(g, l, masked, idx[p], w[p], a.pmp, o[p]);
+        if (good) lw |= 1u << (8 * p);
+        else if (n0 + p >= 0 && n0 + p < a.no) bad = true;
+      }
+      if (all_in) {
+        store4<R>(a.go + ob + n0, o[0], o[1], o[2], o[3]);
+        __stcs(reinterpret_cast<unsigned*>(a.lo + ob + n0), lw);
+      } else {
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+          if (n0 + p >= 0 && n0 + p < a.no) { a.go[ob + n0 + p] = o[p]; a.lo[ob + n0 + p] = (u8)((lw >> (8 * p)) & 1u); }
+      }
+      if (bad) a.flag[k] = 1;
+    }
+  }
+}
+
+// The streaming kernel needs go and lo to share their 4-element phase (true for any pair of
+// allocations aligned to 16 bytes) and does not implement the spiral search.
+template <class R> bool fast_bilinear_ok(const Plan<R>& P, const FieldArgs<R>& a) {
+  if (P.method != M_BILINEAR || P.vec || a.mspiral > 0 || P.no <= 0) return false;
+  const uintptr_t g = reinterpret_cast<uintptr_t>(a.go), l = reinterpret_cast<uintptr_t>(a.lo);
+  if (g % sizeof(R)) return false;
+  return ((g / sizeof(R)) & 3) == (l & 3);
+}
+
+template <class R> void launch_fast_bilinear(const Plan<R>& P, const FieldArgs<R>& a, cudaStream_t st) {
+  constexpr int KPT = 32;
+  const int base_mis = (int)(reinterpret_cast<uintptr_t>(a.lo) & 3);
+  const int nthreads = a.no / 4 + 2;
+  const int per_class = (a.kc + 3) / 4;
+  dim3 grid(4 * nblk(per_class, KPT), nblk(nthreads, 128));
+  k_bilinear_stream<R, KPT><<<grid, 128, 0, st>>>(a, P.nxy, P.wxy, base_mis);
+  g_launches++;
+}
+
 }  // namespace ipb

@@ -12,6 +12,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <vector>
@@ -77,6 +78,8 @@ template <class R> struct Plan {
   int npn = 0, nps = 0;
   int *pole_n = nullptr, *pole_s = nullptr;  // 0-based output indices, ascending
   R *pclon_n = nullptr, *pslon_n = nullptr, *pclon_s = nullptr, *pslon_s = nullptr;
+  // 1-based range of input-field positions any tap refers to (host calls copy only this window)
+  int src_lo = 1, src_hi = 0;
   size_t bytes = 0;
   double build_ms = 0;
 
@@ -298,6 +301,17 @@ template <class R> __global__ void k_pole_trig(int np, const int* __restrict__ i
   slon[q] = DM<R>::sin(l / dpr);
 }
 
+// Range of the 1-based input positions referenced by a tap array (zeros = "outside" are skipped).
+static __global__ void k_idx_range(const int* __restrict__ idx, size_t n, int* lohi) {
+  int lo = 0x7fffffff, hi = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int v = idx[i];
+    if (v > 0) { lo = min(lo, v); hi = max(hi, v); }
+  }
+  for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+  if ((threadIdx.x & 31) == 0 && hi > 0) { atomicMin(lohi, lo); atomicMax(lohi + 1, hi); }
+}
+
 // ---- host: option decode ---------------------------------------------------------------------
 // Returns iret contribution (0 or 32) and fills bo.  `vec_wb_quirk`: budget vector picks WB from
 // IPOPT(2) directly (budget_interp_mod.F90:571-575) instead of LSW.
@@ -396,11 +410,11 @@ Plan<R>* build_plan(int method, bool vec, const i64* ipopt, const GridHost<R>& g
   if (vec) { P->crot = dalloc<R>(mo); P->srot = dalloc<R>(mo); }
   P->bytes += (size_t)mo * sizeof(R) * (vec ? 6 : 4);
   if (station) {
-    IPB_CUDA(cudaMemcpyAsync(P->rlat, st_lat, mo * sizeof(R), cudaMemcpyHostToDevice, st));
-    IPB_CUDA(cudaMemcpyAsync(P->rlon, st_lon, mo * sizeof(R), cudaMemcpyHostToDevice, st));
+    IPB_CUDA(cudaMemcpyAsync(P->rlat, st_lat, mo * sizeof(R), cudaMemcpyDefault, st));
+    IPB_CUDA(cudaMemcpyAsync(P->rlon, st_lon, mo * sizeof(R), cudaMemcpyDefault, st));
     if (vec) {
-      IPB_CUDA(cudaMemcpyAsync(P->crot, st_crot, mo * sizeof(R), cudaMemcpyHostToDevice, st));
-      IPB_CUDA(cudaMemcpyAsync(P->srot, st_srot, mo * sizeof(R), cudaMemcpyHostToDevice, st));
+      IPB_CUDA(cudaMemcpyAsync(P->crot, st_crot, mo * sizeof(R), cudaMemcpyDefault, st));
+      IPB_CUDA(cudaMemcpyAsync(P->srot, st_srot, mo * sizeof(R), cudaMemcpyDefault, st));
     }
   }
   int* d_cnt = dalloc<int>(2);
@@ -510,6 +524,23 @@ Plan<R>* build_plan(int method, bool vec, const i64* ipopt, const GridHost<R>& g
     up(ps, P->pole_s, P->pclon_s, P->pslon_s);
   }
   dfree(d_cnt);
+  {  // source window actually referenced by the plan
+    const int* taps = budget ? P->bn : P->nxy;
+    const size_t ntap = budget ? (size_t)P->bo.nsamp * (nbud ? 1 : 4) * no : (size_t)P->nt * no;
+    P->src_lo = 1; P->src_hi = 0;
+    if (taps && ntap > 0) {
+      int* d_lohi = dalloc<int>(2);
+      const int init[2] = {0x7fffffff, 0};
+      IPB_CUDA(cudaMemcpyAsync(d_lohi, init, sizeof(init), cudaMemcpyHostToDevice, st));
+      k_idx_range<<<std::min(nblk((long long)ntap, 256), 148 * 8), 256, 0, st>>>(taps, ntap, d_lohi);
+      g_launches++;
+      int lohi[2];
+      IPB_CUDA(cudaMemcpyAsync(lohi, d_lohi, sizeof(lohi), cudaMemcpyDeviceToHost, st));
+      IPB_CUDA(cudaStreamSynchronize(st));
+      dfree(d_lohi);
+      if (lohi[1] > 0) { P->src_lo = lohi[0]; P->src_hi = lohi[1]; }
+    }
+  }
   P->iret = iret;
   cudaEventRecord(e1, st);
   cudaEventSynchronize(e1);
