@@ -3,6 +3,7 @@
 Three translation units (the C ABI and one instantiation of the kernels per real kind) are compiled
 in parallel and linked into one shared library next to this file.
 """
+import hashlib
 import os
 import subprocess
 from concurrent.futures import ThreadPoolExecutor
@@ -25,15 +26,26 @@ def sources():
     return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
 
 
-def up_to_date():
-    if not os.path.exists(OUT):
+STAMP = os.path.join(OBJ, "libipb200.sha256")
+
+
+def source_digest(extra=()):
+    """Content hash of every source and of the flags: file times do not survive the copy to a GPU box."""
+    h = hashlib.sha256(" ".join(NVCC_FLAGS + list(extra)).encode())
+    for s in sources():
+        h.update(os.path.basename(s).encode())
+        h.update(open(s, "rb").read())
+    return h.hexdigest()
+
+
+def up_to_date(extra=()):
+    if not (os.path.exists(OUT) and os.path.exists(STAMP)):
         return False
-    t = os.path.getmtime(OUT)
-    return all(os.path.getmtime(s) <= t for s in sources())
+    return open(STAMP).read().strip() == source_digest(extra)
 
 
 def build_library(force=False, verbose=False, extra=()):
-    if not force and up_to_date():
+    if not force and up_to_date(extra):
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(OBJ, exist_ok=True)
@@ -56,4 +68,6 @@ def build_library(force=False, verbose=False, extra=()):
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)
+    with open(STAMP, "w") as f:
+        f.write(source_digest(extra) + "\n")
     return OUT

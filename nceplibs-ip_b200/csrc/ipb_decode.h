@@ -13,6 +13,7 @@
 #include <type_traits>
 #include <vector>
 
+#include "ipb_crmath.h"
 #include "ipb_grid.h"
 
 namespace ipb {
@@ -21,14 +22,14 @@ namespace ipb {
 #define IPB_RC(x) (std::is_same<R, float>::value ? (R)(x##f) : (R)(x))
 
 // Host math in kind R.  For R=float every transcendental is evaluated in binary64 and rounded
-// once to binary32 — the same definition the device code uses (ipb_math.cuh).
+// once to binary32 — the same definition the device code uses; binary64 evaluations are correctly rounded (ipb_crmath.h).
 template <class R> struct HM {
-  static R sin(R x) { return (R)::sin((double)x); }
-  static R cos(R x) { return (R)::cos((double)x); }
-  static R tan(R x) { return (R)::tan((double)x); }
-  static R asin(R x) { return (R)::asin((double)x); }
-  static R log(R x) { return (R)::log((double)x); }
-  static R pow(R a, R b) { return (R)::pow((double)a, (double)b); }
+  static R sin(R x) { return (R)cr::sin((double)x); }
+  static R cos(R x) { return (R)cr::cos((double)x); }
+  static R tan(R x) { return (R)cr::tan((double)x); }
+  static R asin(R x) { return (R)cr::asin((double)x); }
+  static R log(R x) { return (R)cr::log((double)x); }
+  static R pow(R a, R b) { return (R)cr::pow((double)a, (double)b); }
   static R sqrt(R x) { return (R)::sqrt((double)x); }  // exact for float via double
   static R fmod(R a, R b) { return (R)::fmod((double)a, (double)b); }  // exact
   static R abs(R x) { return x < 0 ? -x : x; }
@@ -211,7 +212,7 @@ template <class R> void gaussian_latitudes(i64 jmax, std::vector<R>& slat, std::
   std::vector<double> z(jh), pk(jh), pkm1(jh), pkm2(jh);
   for (i64 j = 0; j < jh; j++) {
     const R arg = (j < 50) ? bz((int)j) * rr : (bz(49) + (R)(j + 1 - 50) * pi) * rr;
-    z[j] = (double)(R)::cos((double)arg);
+    z[j] = (double)(R)cr::cos((double)arg);
   }
   const double eps = 10. * std::numeric_limits<double>::epsilon();
   for (double spmax = 1.; spmax > eps;) {
@@ -277,14 +278,14 @@ template <class R> void finish_gaussian(GridHost<R>& gh, const Raw<R>& r) {
 // Rotate a geographic point into the rotated system (used by the GRIB1 decode of both
 // rotated grids: ip_rot_equid_cylind_grid_mod.F90:95-120, ip_rot_equid_cylind_egrid_mod.F90:116-128).
 inline void to_rotated(double rlat, double rlon, double rlon0, double slat0, double clat0, double dpr, double& rlatr, double& rlonr) {
-  const double slat = ::sin(rlat / dpr), clat = ::cos(rlat / dpr);
+  const double slat = cr::sin(rlat / dpr), clat = cr::cos(rlat / dpr);
   const double hs = std::copysign(1., ::fmod(rlon - rlon0 + 180 + 3600, 360.) - 180);
-  const double clon = ::cos((rlon - rlon0) / dpr);
+  const double clon = cr::cos((rlon - rlon0) / dpr);
   const double slatr = clat0 * slat - slat0 * clat * clon;
   const double clatr = ::sqrt(1 - slatr * slatr);
   const double clonr = (clat0 * clat * clon + slat0 * slat) / clatr;
-  rlatr = dpr * ::asin(slatr);
-  rlonr = hs * dpr * ::acos(clonr);
+  rlatr = dpr * cr::asin(slatr);
+  rlonr = hs * dpr * cr::acos(clonr);
 }
 
 }  // namespace detail
@@ -321,7 +322,7 @@ template <class R> GridHost<R> decode_grib1(const i64* k) {
       p.irot = (int)bit(k[5], 8); p.hid = bit(k[10], 128) ? -1. : 1.;
       const double rlat1 = (double)k[3] * 1.E-3, rlon1 = (double)k[4] * 1.E-3, rlat0 = (double)k[6] * 1.E-3;
       p.rlon0 = (double)k[7] * 1.E-3;
-      p.slat0 = ::sin(rlat0 / dprd); p.clat0 = ::cos(rlat0 / dprd);
+      p.slat0 = cr::sin(rlat0 / dprd); p.clat0 = cr::cos(rlat0 / dprd);
       double rlatr, rlonr;
       to_rotated(rlat1, rlon1, p.rlon0, p.slat0, p.clat0, dprd, rlatr, rlonr);
       p.dlats = rlatr / (double)(-((p.jm - 1) / 2));
@@ -335,7 +336,7 @@ template <class R> GridHost<R> decode_grib1(const i64* k) {
       const double rlat1 = (double)k[3] * 1.E-3, rlon1 = (double)k[4] * 1.E-3, rlat0 = (double)k[6] * 1.E-3;
       const double rlat2 = (double)k[11] * 1.E-3, rlon2 = (double)k[12] * 1.E-3;
       p.rlon0 = (double)k[7] * 1.E-3;
-      p.slat0 = ::sin(rlat0 / dprd); p.clat0 = ::cos(rlat0 / dprd);
+      p.slat0 = cr::sin(rlat0 / dprd); p.clat0 = cr::cos(rlat0 / dprd);
       double nbd, ebd;
       to_rotated(rlat1, rlon1, p.rlon0, p.slat0, p.clat0, dprd, p.sbd, p.wbd);
       to_rotated(rlat2, rlon2, p.rlon0, p.slat0, p.clat0, dprd, nbd, ebd);
@@ -409,7 +410,7 @@ template <class R> GridHost<R> decode_grib2(i64 num, const i64* t, i64 len) {
       const double rlat0 = (double)scaled(t[19]) + 90.0;
       p.rlon0 = (double)scaled(t[20]);
       const double rlat2 = (double)scaled(t[14]), rlon2 = (double)scaled(t[15]);
-      p.slat0 = ::sin(rlat0 / dprd); p.clat0 = ::cos(rlat0 / dprd);
+      p.slat0 = cr::sin(rlat0 / dprd); p.clat0 = cr::cos(rlat0 / dprd);
       p.wbd = rlon1; if (p.wbd > 180.0) p.wbd = p.wbd - 360.0;
       p.sbd = rlat1;
       p.dlats = (rlat2 - p.sbd) / (double)(R)(p.jm - 1);
@@ -426,7 +427,7 @@ template <class R> GridHost<R> decode_grib2(i64 num, const i64* t, i64 len) {
       p.dlats = (double)scaled(t[17]);
       p.dlons = (double)scaled(t[16]) * 0.5;
       const double rlat0 = (double)scaled(t[19]) + 90.0;
-      p.slat0 = ::sin(rlat0 / dprd); p.clat0 = ::cos(rlat0 / dprd);
+      p.slat0 = cr::sin(rlat0 / dprd); p.clat0 = cr::cos(rlat0 / dprd);
       p.sbd = (double)scaled(t[11]);
       p.wbd = (double)scaled(t[12]); if (p.wbd > 180.0) p.wbd -= 360.0;
       plain_window(p, (i64)p.im * 2 - 1 + 1);

@@ -10,11 +10,13 @@
 // constants precomputed in GridP (ipb_decode.h).
 //
 // Arithmetic contract: compiled with -fmad=false; R=float rounds every +,-,*,/ to binary32 and
-// defines each transcendental as "binary64 evaluation rounded once" (DM<float>); the rotated
+// defines each transcendental as "correctly rounded binary64 evaluation (ipb_crmath.h) rounded once
+// more" (DM<float>); R=double uses the correctly rounded functions directly; the rotated
 // grids compute in binary64 for both kinds, like the reference's real64 internals.
 #pragma once
 #include <cuda_runtime.h>
 
+#include "ipb_crmath.h"
 #include "ipb_grid.h"
 
 namespace ipb {
@@ -22,15 +24,15 @@ namespace ipb {
 #define IPB_DL(x) (sizeof(R) == 4 ? (R)(x##f) : (R)(x))
 
 template <class R> struct DM {
-  static __device__ __forceinline__ R sin(R x) { return (R)::sin((double)x); }
-  static __device__ __forceinline__ R cos(R x) { return (R)::cos((double)x); }
-  static __device__ __forceinline__ R tan(R x) { return (R)::tan((double)x); }
-  static __device__ __forceinline__ R asin(R x) { return (R)::asin((double)x); }
-  static __device__ __forceinline__ R atan(R x) { return (R)::atan((double)x); }
-  static __device__ __forceinline__ R atan2(R y, R x) { return (R)::atan2((double)y, (double)x); }
-  static __device__ __forceinline__ R log(R x) { return (R)::log((double)x); }
-  static __device__ __forceinline__ R exp(R x) { return (R)::exp((double)x); }
-  static __device__ __forceinline__ R pow(R a, R b) { return (R)::pow((double)a, (double)b); }
+  static __device__ __forceinline__ R sin(R x) { return (R)cr::sin((double)x); }
+  static __device__ __forceinline__ R cos(R x) { return (R)cr::cos((double)x); }
+  static __device__ __forceinline__ R tan(R x) { return (R)cr::tan((double)x); }
+  static __device__ __forceinline__ R asin(R x) { return (R)cr::asin((double)x); }
+  static __device__ __forceinline__ R atan(R x) { return (R)cr::atan((double)x); }
+  static __device__ __forceinline__ R atan2(R y, R x) { return (R)cr::atan2((double)y, (double)x); }
+  static __device__ __forceinline__ R log(R x) { return (R)cr::log((double)x); }
+  static __device__ __forceinline__ R exp(R x) { return (R)cr::exp((double)x); }
+  static __device__ __forceinline__ R pow(R a, R b) { return (R)cr::pow((double)a, (double)b); }
   static __device__ __forceinline__ R sqrt(R x) { return (R)::sqrt((double)x); }
   static __device__ __forceinline__ R fmod(R a, R b) { return (R)::fmod((double)a, (double)b); }
   static __device__ __forceinline__ R abs(R x) { return x < 0 ? -x : x; }
@@ -200,7 +202,7 @@ __device__ __forceinline__ void rot_ext(const GridP<R>& g, R fill, R rlon, const
     if (g.irot == 1) {
       if (s.clatr <= 0.) { e.crot = (R)(-::copysign(1., s.slatr * g.slat0)); e.srot = IPB_DL(0.); }
       else {
-        const double slon = ::sin(((double)rlon - g.rlon0) / dpr);
+        const double slon = cr::sin(((double)rlon - g.rlon0) / dpr);
         e.crot = (R)((g.clat0 * s.clat + g.slat0 * s.slat * s.clon) / s.clatr);
         e.srot = (R)(g.slat0 * slon / s.clatr);
       }
@@ -208,7 +210,7 @@ __device__ __forceinline__ void rot_ext(const GridP<R>& g, R fill, R rlon, const
   }
   if (EXT >= EXT_ALL) {
     if (s.clatr <= 0.) { e.xlon = e.xlat = e.ylon = e.ylat = fill; e.area = fill; return; }
-    const double slon = ::sin(((double)rlon - g.rlon0) / dpr);
+    const double slon = cr::sin(((double)rlon - g.rlon0) / dpr);
     const double t1 = (g.clat0 * s.clat + g.slat0 * s.slat * s.clon) / s.clatr;
     const double t2 = g.slat0 * slon / s.clatr;
     const double xlo = t1 * s.clat / (g.dlons * s.clatr), xla = -t2 / (g.dlons * s.clatr);
@@ -216,7 +218,7 @@ __device__ __forceinline__ void rot_ext(const GridP<R>& g, R fill, R rlon, const
     const double re = (double)g.rerth;
     if (g.type == P_ROTB) {
       e.xlon = (R)xlo; e.xlat = (R)xla; e.ylon = (R)ylo; e.ylat = (R)yla;
-      e.area = (R)(2. * (re * re) * s.clatr * (g.dlons / dpr) * ::sin(0.5 * g.dlats / dpr));
+      e.area = (R)(2. * (re * re) * s.clatr * (g.dlons / dpr) * cr::sin(0.5 * g.dlats / dpr));
     } else {
       e.xlon = (R)(xlo - ylo); e.xlat = (R)(xla - yla); e.ylon = (R)(xlo + ylo); e.ylat = (R)(xla + yla);
       e.area = (R)(re * re * s.clatr * g.dlats * g.dlons) * IPB_DL(2.) / (DM<R>::dpr() * DM<R>::dpr());
@@ -340,19 +342,19 @@ __device__ bool proj_fwd(const GridP<R>& g, R fill, R x, R y, R& rlon, R& rlat, 
         }
       }
       pd::RotPt s;
-      const double clonr = ::cos(rlonr / dprd);
-      s.slatr = ::sin(rlatr / dprd);
-      s.clatr = ::cos(rlatr / dprd);
+      const double clonr = cr::cos(rlonr / dprd);
+      s.slatr = cr::sin(rlatr / dprd);
+      s.clatr = cr::cos(rlatr / dprd);
       s.slat = g.clat0 * s.slatr + g.slat0 * s.clatr * clonr;
       if (s.slat <= -1 || s.slat >= 1) {
-        s.clat = 0.; s.clon = ::cos(g.rlon0 / dprd);
+        s.clat = 0.; s.clon = cr::cos(g.rlon0 / dprd);
         rlon = IPB_DL(0.); rlat = (s.slat <= -1) ? IPB_DL(-90.) : IPB_DL(90.);
       } else {
         s.clat = ::sqrt(1 - s.slat * s.slat);
         s.clon = (g.clat0 * s.clatr * clonr - g.slat0 * s.slatr) / s.clat;
         s.clon = ::fmin(::fmax(s.clon, -1.), 1.);
-        rlon = (R)::fmod(g.rlon0 + hs * dprd * ::acos(s.clon) + 3600, 360.);
-        rlat = (R)(dprd * ::asin(s.slat));
+        rlon = (R)::fmod(g.rlon0 + hs * dprd * cr::acos(s.clon) + 3600, 360.);
+        rlat = (R)(dprd * cr::asin(s.slat));
       }
       pd::rot_ext<R, EXT>(g, fill, rlon, s, e);
       return true;
@@ -443,9 +445,9 @@ __device__ bool proj_inv(const GridP<R>& g, R fill, R rlon, R rlat, R& x, R& y, 
       const double dprd = (double)dpr;
       pd::RotPt s;
       const double hs = ::copysign(1., ::fmod((double)rlon - g.rlon0 + 180 + 3600, 360.) - 180);
-      s.clon = ::cos(((double)rlon - g.rlon0) / dprd);
-      s.slat = ::sin((double)rlat / dprd);
-      s.clat = ::cos((double)rlat / dprd);
+      s.clon = cr::cos(((double)rlon - g.rlon0) / dprd);
+      s.slat = cr::sin((double)rlat / dprd);
+      s.clat = cr::cos((double)rlat / dprd);
       s.slatr = g.clat0 * s.slat - g.slat0 * s.clat * s.clon;
       double rlonr, rlatr;
       if (s.slatr <= -1 || s.slatr >= 1) { s.clatr = 0.; rlonr = 0.; rlatr = (s.slatr <= -1) ? -90. : 90.; }
@@ -453,8 +455,8 @@ __device__ bool proj_inv(const GridP<R>& g, R fill, R rlon, R rlat, R& x, R& y, 
         s.clatr = ::sqrt(1 - s.slatr * s.slatr);
         double clonr = (g.clat0 * s.clat * s.clon + g.slat0 * s.slat) / s.clatr;
         clonr = ::fmin(::fmax(clonr, -1.), 1.);
-        rlonr = hs * dprd * ::acos(clonr);
-        rlatr = dprd * ::asin(s.slatr);
+        rlonr = hs * dprd * cr::acos(clonr);
+        rlatr = dprd * cr::asin(s.slatr);
       }
       R xf, yf;
       if (eg && g.is_grib2) {
@@ -491,10 +493,10 @@ template <class R> __device__ __forceinline__ bool valid_xy(R x, R y) {
 template <class R> __device__ __forceinline__ void movect(R flat, R flon, R tlat, R tlon, R& crot, R& srot) {
   const double crdlim = (double)IPB_DL(0.9999999);
   const double dpr = 180. / (double)IPB_DL(3.14159265358979);
-  const double ctlat = ::cos((double)tlat / dpr), stlat = ::sin((double)tlat / dpr);
-  const double cflat = ::cos((double)flat / dpr), sflat = ::sin((double)flat / dpr);
+  const double ctlat = cr::cos((double)tlat / dpr), stlat = cr::sin((double)tlat / dpr);
+  const double cflat = cr::cos((double)flat / dpr), sflat = cr::sin((double)flat / dpr);
   const double dl = (double)(flon - tlon) / dpr;
-  const double cdlon = ::cos(dl), sdlon = ::sin(dl);
+  const double cdlon = cr::cos(dl), sdlon = cr::sin(dl);
   const double crd = stlat * sflat + ctlat * cflat * cdlon;
   if (::fabs(crd) <= crdlim) {
     const double srd2rn = -1 / (1 - crd * crd);

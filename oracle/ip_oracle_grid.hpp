@@ -12,8 +12,9 @@
 // Arithmetic contract ("kind"): R = float reproduces the _4 build (every +,-,*,/ rounded to
 // fp32, no FMA contraction: compile with -ffp-contract=off), R = double the _d/_8 builds.
 // Transcendentals in the _4 kind are defined as "evaluate in binary64, round once to
-// binary32" (SURVEY.md §7 hard part 1, option a) so that the CPU oracle and the CUDA kernels
-// can agree bit-for-bit up to double-rounding tie points.
+// binary32" (SURVEY.md §7 hard part 1, option a); binary64 evaluations go through
+// ip_oracle_libm.hpp (correctly rounded by default, plain glibc in the _glibc flavour) so that
+// the CPU oracle and the CUDA kernels can agree bit-for-bit.
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -23,6 +24,8 @@
 #include <limits>
 #include <type_traits>
 #include <vector>
+
+#include "ip_oracle_libm.hpp"
 
 namespace ipo {
 
@@ -34,16 +37,16 @@ typedef long long i64;
 // ---- math in kind R ---------------------------------------------------------------------
 template <class R> struct M;
 template <> struct M<float> {
-  static float sin(float x) { return (float)::sin((double)x); }
-  static float cos(float x) { return (float)::cos((double)x); }
-  static float tan(float x) { return (float)::tan((double)x); }
-  static float asin(float x) { return (float)::asin((double)x); }
-  static float acos(float x) { return (float)::acos((double)x); }
-  static float atan(float x) { return (float)::atan((double)x); }
-  static float atan2(float y, float x) { return (float)::atan2((double)y, (double)x); }
-  static float log(float x) { return (float)::log((double)x); }
-  static float exp(float x) { return (float)::exp((double)x); }
-  static float pow(float a, float b) { return (float)::pow((double)a, (double)b); }
+  static float sin(float x) { return (float)lm::sin((double)x); }
+  static float cos(float x) { return (float)lm::cos((double)x); }
+  static float tan(float x) { return (float)lm::tan((double)x); }
+  static float asin(float x) { return (float)lm::asin((double)x); }
+  static float acos(float x) { return (float)lm::acos((double)x); }
+  static float atan(float x) { return (float)lm::atan((double)x); }
+  static float atan2(float y, float x) { return (float)lm::atan2((double)y, (double)x); }
+  static float log(float x) { return (float)lm::log((double)x); }
+  static float exp(float x) { return (float)lm::exp((double)x); }
+  static float pow(float a, float b) { return (float)lm::pow((double)a, (double)b); }
   static float sqrt(float x) { return ::sqrtf(x); }
   static float fmod(float a, float b) { return ::fmodf(a, b); }
   static float fabs(float x) { return ::fabsf(x); }
@@ -52,16 +55,16 @@ template <> struct M<float> {
   static float huge() { return std::numeric_limits<float>::max(); }
 };
 template <> struct M<double> {
-  static double sin(double x) { return ::sin(x); }
-  static double cos(double x) { return ::cos(x); }
-  static double tan(double x) { return ::tan(x); }
-  static double asin(double x) { return ::asin(x); }
-  static double acos(double x) { return ::acos(x); }
-  static double atan(double x) { return ::atan(x); }
-  static double atan2(double y, double x) { return ::atan2(y, x); }
-  static double log(double x) { return ::log(x); }
-  static double exp(double x) { return ::exp(x); }
-  static double pow(double a, double b) { return ::pow(a, b); }
+  static double sin(double x) { return lm::sin(x); }
+  static double cos(double x) { return lm::cos(x); }
+  static double tan(double x) { return lm::tan(x); }
+  static double asin(double x) { return lm::asin(x); }
+  static double acos(double x) { return lm::acos(x); }
+  static double atan(double x) { return lm::atan(x); }
+  static double atan2(double y, double x) { return lm::atan2(y, x); }
+  static double log(double x) { return lm::log(x); }
+  static double exp(double x) { return lm::exp(x); }
+  static double pow(double a, double b) { return lm::pow(a, b); }
   static double sqrt(double x) { return ::sqrt(x); }
   static double fmod(double a, double b) { return ::fmod(a, b); }
   static double fabs(double x) { return ::fabs(x); }
@@ -393,14 +396,14 @@ template <class R> bool init_grid_grib1(Grid<R>& g, const i64* k /*200 words*/) 
       g.kscan = (int)imod(k[10] / 256, 2);
       i64 iscan = imod(k[10] / 128, 2);
       double hi = iscan ? -1. : 1.;
-      double slat1 = ::sin(rlat1 / dprd), clat1 = ::cos(rlat1 / dprd), slat0 = ::sin(rlat0 / dprd), clat0 = ::cos(rlat0 / dprd);
+      double slat1 = lm::sin(rlat1 / dprd), clat1 = lm::cos(rlat1 / dprd), slat0 = lm::sin(rlat0 / dprd), clat0 = lm::cos(rlat0 / dprd);
       double hs = std::copysign(1., ::fmod(rlon1 - rlon0 + 180 + 3600, 360.) - 180);
-      double clon1 = ::cos((rlon1 - rlon0) / dprd);
+      double clon1 = lm::cos((rlon1 - rlon0) / dprd);
       double slatr = clat0 * slat1 - slat0 * clat1 * clon1;
       double clatr = ::sqrt(1 - slatr * slatr);
       double clonr = (clat0 * clat1 * clon1 + slat0 * slat1) / clatr;
-      double rlatr = dprd * ::asin(slatr);
-      double rlonr = hs * dprd * ::acos(clonr);
+      double rlatr = dprd * lm::asin(slatr);
+      double rlonr = hs * dprd * lm::acos(clonr);
       g.dlats = rlatr / (double)(-((jm - 1) / 2));
       g.dlons = rlonr / (double)(-(((im * 2 - 1) - 1) / 2));
       g.im = im; g.jm = jm; g.rlon0 = rlon0; g.rlon1d = rlon1; g.rlat1d = rlat1; g.clat0 = clat0; g.slat0 = slat0; g.hid = hi;
@@ -413,24 +416,24 @@ template <class R> bool init_grid_grib1(Grid<R>& g, const i64* k /*200 words*/) 
       g.rlon0 = (double)k[7] * 1.E-3;
       double rlat2 = (double)k[11] * 1.E-3, rlon2 = (double)k[12] * 1.E-3;
       g.irot = (int)imod(k[5] / 8, 2); g.im = k[1]; g.jm = k[2];
-      double slat1 = ::sin(rlat1 / dprd), clat1 = ::cos(rlat1 / dprd);
-      g.slat0 = ::sin(rlat0 / dprd); g.clat0 = ::cos(rlat0 / dprd);
+      double slat1 = lm::sin(rlat1 / dprd), clat1 = lm::cos(rlat1 / dprd);
+      g.slat0 = lm::sin(rlat0 / dprd); g.clat0 = lm::cos(rlat0 / dprd);
       double hs = std::copysign(1., ::fmod(rlon1 - g.rlon0 + 180 + 3600, 360.) - 180);
-      double clon1 = ::cos((rlon1 - g.rlon0) / dprd);
+      double clon1 = lm::cos((rlon1 - g.rlon0) / dprd);
       double slatr = g.clat0 * slat1 - g.slat0 * clat1 * clon1;
       double clatr = ::sqrt(1 - slatr * slatr);
       double clonr = (g.clat0 * clat1 * clon1 + g.slat0 * slat1) / clatr;
-      double rlatr = dprd * ::asin(slatr);
-      double rlonr = hs * dprd * ::acos(clonr);
+      double rlatr = dprd * lm::asin(slatr);
+      double rlonr = hs * dprd * lm::acos(clonr);
       g.wbd = rlonr; g.sbd = rlatr;
-      double slat2 = ::sin(rlat2 / dprd), clat2 = ::cos(rlat2 / dprd);
+      double slat2 = lm::sin(rlat2 / dprd), clat2 = lm::cos(rlat2 / dprd);
       double hs2 = std::copysign(1., ::fmod(rlon2 - g.rlon0 + 180 + 3600, 360.) - 180);
-      double clon2 = ::cos((rlon2 - g.rlon0) / dprd);
+      double clon2 = lm::cos((rlon2 - g.rlon0) / dprd);
       slatr = g.clat0 * slat2 - g.slat0 * clat2 * clon2;
       clatr = ::sqrt(1 - slatr * slatr);
       clonr = (g.clat0 * clat2 * clon2 + g.slat0 * slat2) / clatr;
-      double nbd = dprd * ::asin(slatr);
-      double ebd = hs2 * dprd * ::acos(clonr);
+      double nbd = dprd * lm::asin(slatr);
+      double ebd = hs2 * dprd * lm::acos(clonr);
       g.dlats = (nbd - g.sbd) / (double)R(g.jm - 1);
       g.dlons = (ebd - g.wbd) / (double)R(g.im - 1);
       g.nscan = (int)imod(k[10] / 32, 2); g.nscan_field_pos = g.nscan; g.kscan = 0;
@@ -543,7 +546,7 @@ template <class R> bool init_grid_grib2(Grid<R>& g, i64 num, const i64* t, i64 l
       g.rlon0 = (double)(R(t[20]) / R(iscale));
       double rlat2 = (double)(R(t[14]) / R(iscale)), rlon2 = (double)(R(t[15]) / R(iscale));
       g.irot = (int)imod(t[13] / 8, 2); g.im = t[7]; g.jm = t[8];
-      g.slat0 = ::sin(rlat0 / dprd); g.clat0 = ::cos(rlat0 / dprd);
+      g.slat0 = lm::sin(rlat0 / dprd); g.clat0 = lm::cos(rlat0 / dprd);
       g.wbd = rlon1; if (g.wbd > 180.0) g.wbd = g.wbd - 360.0;
       g.sbd = rlat1;
       g.dlats = (rlat2 - g.sbd) / (double)R(g.jm - 1);
@@ -566,7 +569,7 @@ template <class R> bool init_grid_grib2(Grid<R>& g, i64 num, const i64* t, i64 l
       g.kscan = (int)imod(t[18] / 8, 2);
       g.hid = imod(t[18] / 128, 2) ? -1. : 1.;
       double rlat0 = (double)(R(t[19]) / R(iscale)); rlat0 = rlat0 + 90.0;
-      g.slat0 = ::sin(rlat0 / dprd); g.clat0 = ::cos(rlat0 / dprd);
+      g.slat0 = lm::sin(rlat0 / dprd); g.clat0 = lm::cos(rlat0 / dprd);
       g.rlat1d = (double)(R(t[11]) / R(iscale)); g.rlon1d = (double)(R(t[12]) / R(iscale));
       setup_rot(g); break;
     }
@@ -615,7 +618,7 @@ template <class R> inline void rot_vect_rot(const Grid<R>& g, const RotState& s,
   if (g.irot == 1) {
     if (s.clatr <= 0.) { crot = R(-std::copysign(1., s.slatr * g.slat0)); srot = 0; }
     else {
-      double slon = ::sin(((double)rlon - g.rlon0) / dprd);
+      double slon = lm::sin(((double)rlon - g.rlon0) / dprd);
       crot = R((g.clat0 * s.clat + g.slat0 * s.slat * s.clon) / s.clatr);
       srot = R(g.slat0 * slon / s.clatr);
     }
@@ -624,7 +627,7 @@ template <class R> inline void rot_vect_rot(const Grid<R>& g, const RotState& s,
 template <class R> inline void rot_map_jacob(const Grid<R>& g, const RotState& s, R fill, R rlon, R& xlon, R& xlat, R& ylon, R& ylat) {
   const double dprd = (double)C<R>::dpr();
   if (s.clatr <= 0.) { xlon = xlat = ylon = ylat = fill; return; }
-  double slon = ::sin(((double)rlon - g.rlon0) / dprd);
+  double slon = lm::sin(((double)rlon - g.rlon0) / dprd);
   double term1 = (g.clat0 * s.clat + g.slat0 * s.slat * s.clon) / s.clatr;
   double term2 = g.slat0 * slon / s.clatr;
   double xlonf = term1 * s.clat / (g.dlons * s.clatr), xlatf = -term2 / (g.dlons * s.clatr);
@@ -636,7 +639,7 @@ template <class R> inline void rot_area(const Grid<R>& g, const RotState& s, R f
   const double dprd = (double)C<R>::dpr();
   const double rerth = (double)g.rerth;
   if (s.clatr <= 0.) { area = fill; return; }
-  if (g.type == G_ROTB) area = R(2. * (rerth * rerth) * s.clatr * (g.dlons / dprd) * ::sin(0.5 * g.dlats / dprd));
+  if (g.type == G_ROTB) area = R(2. * (rerth * rerth) * s.clatr * (g.dlons / dprd) * lm::sin(0.5 * g.dlats / dprd));
   else area = R(rerth * rerth * s.clatr * g.dlats * g.dlons) * RL(2.) / (C<R>::dpr() * C<R>::dpr());
 }
 
@@ -958,18 +961,18 @@ void gdswzd_proj(const Grid<R>& g, int iopt, i64 npts, R fill, R* xpts, R* ypts,
               rlatr = ((double)yf - 1.0) * dlats + sbd;
             }
           }
-          double clonr = ::cos(rlonr / dprd);
-          s.slatr = ::sin(rlatr / dprd);
-          s.clatr = ::cos(rlatr / dprd);
+          double clonr = lm::cos(rlonr / dprd);
+          s.slatr = lm::sin(rlatr / dprd);
+          s.clatr = lm::cos(rlatr / dprd);
           s.slat = clat0 * s.slatr + slat0 * s.clatr * clonr;
-          if (s.slat <= -1) { s.clat = 0.; s.clon = ::cos(rlon0 / dprd); rlon[n] = RL(0.); rlat[n] = RL(-90.); }
-          else if (s.slat >= 1) { s.clat = 0.; s.clon = ::cos(rlon0 / dprd); rlon[n] = RL(0.); rlat[n] = RL(90.); }
+          if (s.slat <= -1) { s.clat = 0.; s.clon = lm::cos(rlon0 / dprd); rlon[n] = RL(0.); rlat[n] = RL(-90.); }
+          else if (s.slat >= 1) { s.clat = 0.; s.clon = lm::cos(rlon0 / dprd); rlon[n] = RL(0.); rlat[n] = RL(90.); }
           else {
             s.clat = ::sqrt(1 - s.slat * s.slat);
             s.clon = (clat0 * s.clatr * clonr - slat0 * s.slatr) / s.clat;
             s.clon = std::min(std::max(s.clon, -1.), 1.);
-            rlon[n] = R(::fmod(rlon0 + hs * dprd * ::acos(s.clon) + 3600, 360.));
-            rlat[n] = R(dprd * ::asin(s.slat));
+            rlon[n] = R(::fmod(rlon0 + hs * dprd * lm::acos(s.clon) + 3600, 360.));
+            rlat[n] = R(dprd * lm::asin(s.slat));
           }
           nret++;
           if (lrot) rot_vect_rot(g, s, rlon[n], o.crot[n], o.srot[n]);
@@ -978,9 +981,9 @@ void gdswzd_proj(const Grid<R>& g, int iopt, i64 npts, R fill, R* xpts, R* ypts,
         } else {
           if (!(M<R>::fabs(rlon[n]) <= RL(360.) && M<R>::fabs(rlat[n]) <= RL(90.))) { xpts[n] = fill; ypts[n] = fill; continue; }
           double hs = std::copysign(1., ::fmod((double)rlon[n] - rlon0 + 180 + 3600, 360.) - 180);
-          s.clon = ::cos(((double)rlon[n] - rlon0) / dprd);
-          s.slat = ::sin((double)rlat[n] / dprd);
-          s.clat = ::cos((double)rlat[n] / dprd);
+          s.clon = lm::cos(((double)rlon[n] - rlon0) / dprd);
+          s.slat = lm::sin((double)rlat[n] / dprd);
+          s.clat = lm::cos((double)rlat[n] / dprd);
           s.slatr = clat0 * s.slat - slat0 * s.clat * s.clon;
           double rlonr, rlatr;
           if (s.slatr <= -1) { s.clatr = 0.; rlonr = 0.; rlatr = -90.; }
@@ -989,8 +992,8 @@ void gdswzd_proj(const Grid<R>& g, int iopt, i64 npts, R fill, R* xpts, R* ypts,
             s.clatr = ::sqrt(1 - s.slatr * s.slatr);
             double clonr = (clat0 * s.clat * s.clon + slat0 * s.slat) / s.clatr;
             clonr = std::min(std::max(clonr, -1.), 1.);
-            rlonr = hs * dprd * ::acos(clonr);
-            rlatr = dprd * ::asin(s.slatr);
+            rlonr = hs * dprd * lm::acos(clonr);
+            rlatr = dprd * lm::asin(s.slatr);
           }
           R xf, yf;
           if (!eg || !g.is_grib2) {

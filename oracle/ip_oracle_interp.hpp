@@ -24,10 +24,10 @@ template <class R> inline void movect(R flat, R flon, R tlat, R tlon, R& crot, R
   const double crdlim = (double)RL(0.9999999);
   const double pi = (double)RL(3.14159265358979);
   const double dpr = 180. / pi;
-  double ctlat = ::cos((double)tlat / dpr), stlat = ::sin((double)tlat / dpr);
-  double cflat = ::cos((double)flat / dpr), sflat = ::sin((double)flat / dpr);
+  double ctlat = lm::cos((double)tlat / dpr), stlat = lm::sin((double)tlat / dpr);
+  double cflat = lm::cos((double)flat / dpr), sflat = lm::sin((double)flat / dpr);
   // FLON-TLON is formed in the default kind before the promotion
-  double cdlon = ::cos((double)(flon - tlon) / dpr), sdlon = ::sin((double)(flon - tlon) / dpr);
+  double cdlon = lm::cos((double)(flon - tlon) / dpr), sdlon = lm::sin((double)(flon - tlon) / dpr);
   double crd = stlat * sflat + ctlat * cflat * cdlon;
   if (std::fabs(crd) <= crdlim) {
     double srd2rn = -1 / (1 - crd * crd);

@@ -1,0 +1,81 @@
+"""CPU-side checks of the boundary and of the arithmetic contract (no GPU needed).
+
+* the C-ABI library loads without a device and exports every symbol include/ipb200.h declares;
+* the product's correctly rounded binary64 functions (csrc/ipb_crmath.h, host build) and the oracle's
+  independent implementation (oracle/ip_oracle_libm.hpp) both equal libquadmath's binary128 result rounded
+  once, on random and adversarial arguments;
+* how far the choice of libm alone moves the reference's results (oracle built with plain glibc vs the
+  correctly rounded oracle): this is the noise floor any cross-platform comparison of the _d kind has.
+"""
+import ctypes as C
+import importlib
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import ipcases as ic
+from oracle_lib import ROOT, oracle
+
+pkg = importlib.import_module("nceplibs-ip_b200")
+
+
+def _declared_symbols():
+    h = open(os.path.join(ROOT, "include", "ipb200.h")).read()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:ipolate[sv]|gdswzd|ipgpu)_[a-z0-9_]+|gdswzd_[4d8])\s*\(", h)))
+
+
+def test_library_exports_every_declared_symbol():
+    pkg.build_library()
+    lib = C.CDLL(pkg.PRODUCT_SO)  # must load without a GPU
+    names = _declared_symbols()
+    assert len(names) >= 3 * 12 + 10, names
+    for kind in "4d8":
+        for stem in ("ipolates_grib2", "ipolates_grib1", "ipolates_grib2_single_field", "ipolates_grib1_single_field",
+                     "ipolatev_grib2", "ipolatev_grib1", "ipolatev_grib2_single_field", "ipolatev_grib1_single_field",
+                     "gdswzd", "gdswzd_grib1", "ipgpu_ipolates_grib2_dev", "ipgpu_ipolatev_grib2_dev"):
+            assert f"{stem}_{kind}" in names, f"{stem}_{kind} not declared"
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    lib.ipgpu_version.restype = C.c_char_p
+    assert b"sm_100a" in lib.ipgpu_version()
+
+
+def test_header_compiles_as_c():
+    src = '#include "ipb200.h"\nint main(void){return 0;}\n'
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), "-x", "c", "-"],
+                       input=src, text=True, capture_output=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_correctly_rounded_functions_match_binary128(tmp_path):
+    exe = str(tmp_path / "crmath_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", os.path.join(ROOT, "tests", "native", "crmath_check.cpp"),
+                           "-lquadmath", "-o", exe])
+    r = subprocess.run([exe, "120000"], capture_output=True, text=True)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout
+
+
+@pytest.mark.parametrize("grid,ip", [("203", 6)])
+def test_libm_sensitivity_of_the_reference_algorithm(grid, ip):
+    """Same algorithm, two libms (glibc 2.39 vs correctly rounded): ipolatev _d results differ by far more than
+    1e-12 on a measurable fraction of points, because movect and the rotated grids amplify 1-ulp differences.
+    Both flavours still pass the reference's own regression tolerance (test_oracle_golden.py)."""
+    kind = "d"
+    gin, gout = ic.g2_input(kind, True), ic.g2_templates(kind, True)[grid]
+    mi, mo = ic.npts_of(gin), ic.npts_of(gout)
+    I = ic.inputs()
+    args = (ip, ic.ipopt_for(ip), gin, gout, mi, mo, 1, [0], np.ones(mi, np.uint8), I["u"], I["v"])
+    a = oracle(kind, "cr").ipolatev(*args)
+    b = oracle(kind, "glibc").ipolatev(*args)
+    assert a["iret"] == b["iret"] == 0 and np.array_equal(a["lo"], b["lo"])
+    scale = np.abs(a["uo"]).max()
+    d = np.abs(a["uo"] - b["uo"]) / scale
+    frac = float(np.mean(d > 1e-12))
+    print(f"grid {grid} ip {ip}: points moved by libm choice > 1e-12: {frac:.3%}, worst {d.max():.3e} (relative to field scale)")
+    assert d.max() < 1e-6   # harmless for any user (the reference's ctest tolerance is 1e-4 absolute) ...
+    assert np.mean(a["uo"] == b["uo"]) < 1.0   # ... but not bit-reproducible across libms
