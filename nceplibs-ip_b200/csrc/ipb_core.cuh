@@ -10,6 +10,7 @@
 
 #include "ipb_apply.cuh"
 #include "ipb_fast.cuh"
+#include "ipb_tiles.cuh"
 #include "ipb_state.h"
 
 namespace ipb {
@@ -52,6 +53,7 @@ void launch_apply(const Plan<R>& P, bool vec, FieldArgs<R> a, cudaStream_t st) {
   const GridP<R>& gi = P.gin.p;
   const int method = P.method;
   if (method == M_BILINEAR || method == M_BICUBIC) {
+    if (method == M_BILINEAR && !vec && tiles_ok(P, a)) { launch_bilinear_tiles(P, a, st); return; }
     if (method == M_BILINEAR && !vec && fast_bilinear_ok(P, a)) { launch_fast_bilinear(P, a, st); return; }
     const int kpb = std::max(1, std::min(a.kc, 16));
     dim3 grid(nblk(no, 128), nblk(a.kc, kpb));
@@ -152,6 +154,7 @@ void run(bool vec, int dev, void* user_stream, i64 ip, const i64* ipopt, const G
   if (!station) { P = cache_find<R>(key); if (P) RT.last_plan_hit = 1; }
   if (!P) {
     P.reset(build_plan<R>(method, vec, ipopt, gin, gout, mi, mo, no, rlat, rlon, crot, srot, st0));
+    if (P->iret == 0 && !station) { build_tile_tables<R>(*P, st0); P->bytes += P->tiles.bytes; }
     if (!station) cache_put<R>(key, P);
   }
   cudaEventRecord(t1, st0);

@@ -54,6 +54,17 @@ struct BudgetOpt {
   std::vector<double> wb;            // per kept sample (small integers; exact in either kind)
 };
 
+// Per-tile cell tables of the staged bilinear kernel (ipb_tiles.cuh), one set per alignment variant.
+struct TileTables {
+  bool ok = false;
+  int ntile = 0, cstride = 0, max_cells = 0;
+  u8* cid[4] = {nullptr, nullptr, nullptr, nullptr};     // [ntile*512] cell number of each point inside its tile (0xff: none)
+  int* ncell[4] = {nullptr, nullptr, nullptr, nullptr};  // [ntile]
+  int* cells[4] = {nullptr, nullptr, nullptr, nullptr};  // [ntile][cstride][4] 1-based source positions of the cell's taps
+  size_t bytes = 0;
+};
+struct TileDev { const u8* cid[4]; const int* ncell[4]; const int* cells[4]; int cstride; };
+
 template <class R> struct Plan {
   std::vector<i64> key;
   int method = 0; bool vec = false; bool to_station = false;
@@ -80,6 +91,7 @@ template <class R> struct Plan {
   R *pclon_n = nullptr, *pslon_n = nullptr, *pclon_s = nullptr, *pslon_s = nullptr;
   // 1-based range of input-field positions any tap refers to (host calls copy only this window)
   int src_lo = 1, src_hi = 0;
+  TileTables tiles;
   size_t bytes = 0;
   double build_ms = 0;
 
@@ -87,6 +99,7 @@ template <class R> struct Plan {
     dfree(d_tab_in); dfree(d_tab_out); dfree(rlat); dfree(rlon); dfree(crot); dfree(srot); dfree(x); dfree(y);
     dfree(nxy); dfree(wxy); dfree(cxy); dfree(sxy); dfree(nc); dfree(bn); dfree(bw); dfree(bc); dfree(bs); dfree(d_wb);
     dfree(pole_n); dfree(pole_s); dfree(pclon_n); dfree(pslon_n); dfree(pclon_s); dfree(pslon_s);
+    for (int v = 0; v < 4; v++) { dfree(tiles.cid[v]); dfree(tiles.ncell[v]); dfree(tiles.cells[v]); }
   }
 };
 
