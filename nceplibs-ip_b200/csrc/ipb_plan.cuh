@@ -58,12 +58,12 @@ struct BudgetOpt {
 struct TileTables {
   bool ok = false;
   int ntile = 0, cstride = 0, max_cells = 0;
-  u8* cid[4] = {nullptr, nullptr, nullptr, nullptr};     // [ntile*512] cell number of each point inside its tile (0xff: none)
+  u8* cid[4] = {nullptr, nullptr, nullptr, nullptr};     // [ntile*128] cell number of each point inside its tile (0xff: none)
   int* ncell[4] = {nullptr, nullptr, nullptr, nullptr};  // [ntile]
   int* cells[4] = {nullptr, nullptr, nullptr, nullptr};  // [ntile][cstride][4] 1-based source positions of the cell's taps
   size_t bytes = 0;
 };
-struct TileDev { const u8* cid[4]; const int* ncell[4]; const int* cells[4]; int cstride; };
+struct TileDev { const u8* cid[4]; const int* ncell[4]; const int* cells[4]; int cstride; int ntile; };
 
 template <class R> struct Plan {
   std::vector<i64> key;

@@ -34,22 +34,29 @@
 // count exceeds the table fall back — per thread and field — to the general code path
 // (bilinear_point, global gathers), which is also what the other kernels use.
 #pragma once
+#include <cstdlib>
+
 #include "ipb_fast.cuh"
 
 namespace ipb {
 
-constexpr int TILE_PTS = 512;   // output points per tile
-constexpr int TILE_THREADS = 128;
+constexpr int TILE_PTS = 128;      // output points per tile: one warp x 4 points
+constexpr int TILE_WARPS = 4;      // independent warp-tiles per block
+constexpr int TILE_THREADS = 32 * TILE_WARPS;
 
 // ---- plan-time: cells of every tile, for one alignment variant ------------------------------------
 // pass 1: per point the number of its cell inside the tile (first-appearance order; 0xff = not a
-// complete 4-tap stencil), per tile the cell count.
+// complete 4-tap stencil), per tile the cell count.  One warp per tile.
 static __global__ void __launch_bounds__(TILE_THREADS)
-k_tile_index(int variant, int no, const int* __restrict__ nxy, u8* __restrict__ cid, int* __restrict__ ncell, int* gmax) {
-  __shared__ int4 tup[TILE_PTS];
-  __shared__ int warp_tot[TILE_THREADS / 32];
-  const int tile = blockIdx.x, tid = threadIdx.x;
-  const int nbase = 4 * (tile * TILE_THREADS + tid) - variant;
+k_tile_index(int variant, int no, int ntile, const int* __restrict__ nxy, u8* __restrict__ cid, int* __restrict__ ncell, int* gmax) {
+  __shared__ int4 tup_all[TILE_WARPS][TILE_PTS];
+  __shared__ int rank_all[TILE_WARPS][TILE_PTS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x * TILE_WARPS + warp;
+  if (tile >= ntile) return;
+  int4* tup = tup_all[warp];
+  int* rank = rank_all[warp];
+  const int nbase = 4 * (tile * 32 + lane) - variant;
   int4 mine[4];
 #pragma unroll
   for (int p = 0; p < 4; p++) {
@@ -60,13 +67,13 @@ k_tile_index(int variant, int no, const int* __restrict__ nxy, u8* __restrict__ 
       if (t.x <= 0 || t.y <= 0 || t.z <= 0 || t.w <= 0) t = make_int4(0, 0, 0, 0);
     }
     mine[p] = t;
-    tup[4 * tid + p] = t;
+    tup[4 * lane + p] = t;
   }
-  __syncthreads();
+  __syncwarp();
   int first[4], nrep = 0;
 #pragma unroll
   for (int p = 0; p < 4; p++) {
-    const int q = 4 * tid + p;
+    const int q = 4 * lane + p;
     first[p] = -1;
     if (mine[p].x > 0) {
       int r = 0;
@@ -78,25 +85,17 @@ k_tile_index(int variant, int no, const int* __restrict__ nxy, u8* __restrict__ 
       if (r == q) nrep++;
     }
   }
-  // exclusive prefix of representative counts over threads
-  int incl = nrep;
+  int incl = nrep;   // inclusive prefix of representative counts over lanes
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += v; }
-  if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
-  __syncthreads();
-  int base = incl - nrep;
-  for (int w = 0; w < (tid >> 5); w++) base += warp_tot[w];
-  // rank of each representative, published through the (now free) .x slot of its tuple
-  __syncthreads();
-  __shared__ int rank[TILE_PTS];
-  int run = base;
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  int run = incl - nrep;
 #pragma unroll
   for (int p = 0; p < 4; p++) {
-    const int q = 4 * tid + p;
+    const int q = 4 * lane + p;
     rank[q] = -1;
     if (first[p] == q) rank[q] = run++;
   }
-  __syncthreads();
+  __syncwarp();
   unsigned packed = 0;
 #pragma unroll
   for (int p = 0; p < 4; p++) {
@@ -104,19 +103,16 @@ k_tile_index(int variant, int no, const int* __restrict__ nxy, u8* __restrict__ 
     if (first[p] >= 0) { const int r = rank[first[p]]; c = r < 0xff ? r : 0xff; }
     packed |= (unsigned)c << (8 * p);
   }
-  reinterpret_cast<unsigned*>(cid)[(size_t)tile * TILE_THREADS + tid] = packed;
-  if (tid == TILE_THREADS - 1) {
-    const int tot = base + nrep;
-    ncell[tile] = tot;
-    atomicMax(gmax, tot);
-  }
+  reinterpret_cast<unsigned*>(cid)[(size_t)tile * 32 + lane] = packed;
+  if (lane == 31) { ncell[tile] = incl; atomicMax(gmax, incl); }
 }
 // pass 2: the cell table itself, [tile][cstride][4] (1-based source positions)
 static __global__ void __launch_bounds__(TILE_THREADS)
-k_tile_cells(int variant, int no, int cstride, const int* __restrict__ nxy, const u8* __restrict__ cid, int* __restrict__ cells) {
-  const int tile = blockIdx.x, tid = threadIdx.x;
-  const int nbase = 4 * (tile * TILE_THREADS + tid) - variant;
-  const unsigned packed = reinterpret_cast<const unsigned*>(cid)[(size_t)tile * TILE_THREADS + tid];
+k_tile_cells(int variant, int no, int ntile, int cstride, const int* __restrict__ nxy, const u8* __restrict__ cid, int* __restrict__ cells) {
+  const int tile = blockIdx.x * TILE_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (tile >= ntile) return;
+  const int nbase = 4 * (tile * 32 + lane) - variant;
+  const unsigned packed = reinterpret_cast<const unsigned*>(cid)[(size_t)tile * 32 + lane];
 #pragma unroll
   for (int p = 0; p < 4; p++) {
     const int n = nbase + p;
@@ -128,19 +124,22 @@ k_tile_cells(int variant, int no, int cstride, const int* __restrict__ nxy, cons
   }
 }
 
+constexpr int TILE_MAX_CELLS = 64;   // staging covers 8*NI cells per tile, NI <= 8
+
 template <class R> void build_tile_tables(Plan<R>& P, cudaStream_t st) {
   TileTables& T = P.tiles;
   T = TileTables();
   if (P.method != M_BILINEAR || P.vec || P.no <= 0 || !P.nxy) return;
   const int no = P.no;
-  const int ng = (no + 3) / 4 + 1;                 // groups, any variant
-  const int ntile = nblk(ng, TILE_THREADS);
+  const int ng = (no + 3) / 4 + 1;                 // groups of 4 points, any variant
+  const int ntile = nblk(ng, 32);
+  const int nb = nblk(ntile, TILE_WARPS);
   int* d_max = dalloc<int>(1);
   IPB_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), st));
   for (int v = 0; v < 4; v++) {
     T.cid[v] = dalloc<u8>((size_t)ntile * TILE_PTS);
     T.ncell[v] = dalloc<int>(ntile);
-    k_tile_index<<<ntile, TILE_THREADS, 0, st>>>(v, no, P.nxy, T.cid[v], T.ncell[v], d_max);
+    k_tile_index<<<nb, TILE_THREADS, 0, st>>>(v, no, ntile, P.nxy, T.cid[v], T.ncell[v], d_max);
     g_launches++;
   }
   int hmax = 0;
@@ -148,14 +147,15 @@ template <class R> void build_tile_tables(Plan<R>& P, cudaStream_t st) {
   IPB_CUDA(cudaStreamSynchronize(st));
   dfree(d_max);
   T.ntile = ntile; T.max_cells = hmax;
-  if (hmax <= 0 || hmax > 254) {                   // too little reuse for staging to pay: general kernel
+  if (hmax <= 0 || hmax > TILE_MAX_CELLS) {        // too little reuse for staging to pay: general kernel
     for (int v = 0; v < 4; v++) { dfree(T.cid[v]); dfree(T.ncell[v]); }
     return;
   }
   T.cstride = hmax;
   for (int v = 0; v < 4; v++) {
     T.cells[v] = dalloc<int>((size_t)ntile * T.cstride * 4);
-    k_tile_cells<<<ntile, TILE_THREADS, 0, st>>>(v, no, T.cstride, P.nxy, T.cid[v], T.cells[v]);
+    IPB_CUDA(cudaMemsetAsync(T.cells[v], 0, (size_t)ntile * T.cstride * 16, st));
+    k_tile_cells<<<nb, TILE_THREADS, 0, st>>>(v, no, ntile, T.cstride, P.nxy, T.cid[v], T.cells[v]);
     g_launches++;
   }
   T.bytes = 4 * ((size_t)ntile * TILE_PTS + (size_t)ntile * 4 + (size_t)ntile * T.cstride * 16);
@@ -167,47 +167,91 @@ template <class R> struct CellRec;   // the four taps of one cell for one field
 template <> struct CellRec<float> { float4 v; __device__ __forceinline__ float get(int t) const { return t == 0 ? v.x : t == 1 ? v.y : t == 2 ? v.z : v.w; } };
 template <> struct CellRec<double> { double2 a, b; __device__ __forceinline__ double get(int t) const { return t == 0 ? a.x : t == 1 ? a.y : t == 2 ? b.x : b.y; } };
 
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+// predicated 4- / 8-byte asynchronous copy global -> shared (straight-line code, no divergent branch)
+__device__ __forceinline__ void cp_async4_if(bool on, void* smem, const void* gmem) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p cp.async.ca.shared.global [%0], [%1], 4;\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem), "r"((int)on));
 }
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+__device__ __forceinline__ void cp_async8_if(bool on, void* smem, const void* gmem) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p cp.async.ca.shared.global [%0], [%1], 8;\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem), "r"((int)on));
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 // Correctly rounded g / w for |w - 1| <= 2^-20, given rw = RN(1/w): q0 = g is within a few ulp,
-// one fused correction makes it faithful, the second correctly rounded (Markstein).  Returns false
-// when g is outside the exponent window in which the residuals are exact (caller divides).
-template <class R> __device__ __forceinline__ bool quot_near1(R g, R w, R rw, R& q) {
+// one fused correction makes it faithful, the second correctly rounded (Markstein).  Valid while the
+// residuals are exact, i.e. g = 0 or |g| inside in_window(); g = -0 gives +0, which is what the
+// reference's sum (it starts from +0) produces.
+template <class R> __device__ __forceinline__ R quot_near1(R g, R w, R rw) {
   R r = fma_r<R>(-g, w, g);
-  R q1 = fma_r<R>(r, rw, g);
+  const R q1 = fma_r<R>(r, rw, g);
   r = fma_r<R>(-q1, w, g);
-  q = fma_r<R>(r, rw, q1);
-  if (sizeof(R) == 4) {
-    const unsigned b = __float_as_uint((float)g);
-    const unsigned t = b + b - 0x28000000u;          // 2*bits - 2*bits(2^-87): exponent window [2^-87, 2^+87)
-    return t < 0xAE000000u || g == (R)0;
-  } else {
-    const unsigned long long b = (unsigned long long)__double_as_longlong((double)g);
-    const unsigned long long t = b + b - 0x3200000000000000ull;   // window [2^-623, 2^+623)
-    return t < 0x9BC0000000000000ull || g == (R)0;
-  }
+  return fma_r<R>(r, rw, q1);
 }
+template <class R> __device__ __forceinline__ R win_lo() { return sizeof(R) == 4 ? (R)6.5e-27f : (R)1e-187; }   // ~2^-87 / 2^-620
+template <class R> __device__ __forceinline__ R win_hi() { return sizeof(R) == 4 ? (R)1.5e26f : (R)1e187; }
+template <class R> __device__ __forceinline__ R abs_r(R x) { return x < 0 ? -x : x; }
 
-// F = fields staged per pass, NI = staging loads per thread and field (covers 128*NI/4 cells).
+// F = fields staged per pass, NI = staging copies per lane and field (covers 8*NI cells).
+// Each warp is an independent tile: it stages its own cells into its own shared-memory slice
+// (double buffered: the copies of pass s+1 are in flight while pass s is computed) and never
+// meets a block-wide barrier.
 template <class R, int F, int NI>
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, sizeof(R) == 4 ? 5 : 3)
 k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restrict__ wxy, TileDev T, int base_mis, int kpt) {
-  constexpr int CMAX = TILE_THREADS * NI / 4;       // cells a tile may have
-  __shared__ __align__(16) R sm[F * CMAX * 4];
-  const int cls = blockIdx.x & 3, slice = blockIdx.x >> 2, tile = blockIdx.y, tid = threadIdx.x;
+  constexpr int CMAX = 8 * NI;                      // cells a tile may have
+  constexpr int BUF = F * CMAX * 4;                 // elements per buffer
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  R* sm = reinterpret_cast<R*>(sm_raw) + warp * 2 * BUF;
+  const int cls = blockIdx.x & 3, slice = blockIdx.x >> 2, tile = blockIdx.y * TILE_WARPS + warp;
+  if (tile >= T.ntile) return;
   const int variant = (base_mis + cls * (a.mo & 3)) & 3;
-  const int n0 = 4 * (tile * TILE_THREADS + tid) - variant;
+  const int n0 = 4 * (tile * 32 + lane) - variant;
+  // fields of this warp: k = cls + 4 j, j in [jbeg, jend)
+  const int jbeg = kpt * slice, jend = min(kpt * (slice + 1), (a.kc - cls + 3) / 4);
+  if (jbeg >= jend) return;
+  // ---- staging assignment: entry q = cell*4 + tap of this tile's cell table ----
+  const int ncell = T.ncell[variant][tile];
+  const int* __restrict__ cells = T.cells[variant] + (size_t)tile * T.cstride * 4;
+  const size_t fstep = 4 * (size_t)a.mi;            // elements between consecutive fields of one class
+  const R* gp[NI];                                  // source address of entry i in the next field to stage
+  bool act[NI];
+#pragma unroll
+  for (int i = 0; i < NI; i++) {
+    const int q = lane + 32 * i;
+    act[i] = q < 4 * ncell;
+    gp[i] = a.gi + (size_t)(cls + 4 * jbeg) * a.mi + (act[i] ? cells[q] - 1 : 0);
+  }
+  auto stage = [&](int buf, int j0) {
+    R* dst = sm + buf * BUF + lane;
+    if (j0 + F <= jend) {          // whole pass: straight-line copies
+#pragma unroll
+      for (int f = 0; f < F; f++) {
+#pragma unroll
+        for (int i = 0; i < NI; i++) {
+          if (sizeof(R) == 4) cp_async4_if(act[i], dst + f * CMAX * 4 + 32 * i, gp[i]);
+          else cp_async8_if(act[i], dst + f * CMAX * 4 + 32 * i, gp[i]);
+          gp[i] += fstep;
+        }
+      }
+    } else {                       // ragged last pass
+      for (int f = 0; j0 + f < jend; f++) {
+#pragma unroll
+        for (int i = 0; i < NI; i++) {
+          if (sizeof(R) == 4) cp_async4_if(act[i], dst + f * CMAX * 4 + 32 * i, gp[i]);
+          else cp_async8_if(act[i], dst + f * CMAX * 4 + 32 * i, gp[i]);
+          gp[i] += fstep;
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  stage(0, jbeg);
+  // bit j-jbeg set: field j of this warp carries a bitmap (kpt <= 32)
+  const unsigned maskbits = __ballot_sync(0xffffffffu, (jbeg + lane < jend) && a.ibi[cls + 4 * (jbeg + lane)] != 0);
   // ---- per-thread plan data: weights, weight sums, cell numbers ----
   R w[4][4], W[4], rW[4];
   int coff[4];
   bool full = true;
-  const unsigned packed = reinterpret_cast<const unsigned*>(T.cid[variant])[(size_t)tile * TILE_THREADS + tid];
+  const unsigned packed = reinterpret_cast<const unsigned*>(T.cid[variant])[(size_t)tile * 32 + lane];
 #pragma unroll
   for (int p = 0; p < 4; p++) {
     const int n = n0 + p;
@@ -222,64 +266,49 @@ k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restric
     const R dev = ws - (R)1;
     full = full && in && c != 0xff && ws >= a.pmp && dev <= (R)9.5e-7 && dev >= (R)-9.5e-7;
   }
-  // ---- staging assignment: entry q = cell*4 + tap of this tile's cell table ----
-  const int ncell = T.ncell[variant][tile];
-  const int* __restrict__ cells = T.cells[variant] + (size_t)tile * T.cstride * 4;
-  int sidx[NI];
-#pragma unroll
-  for (int i = 0; i < NI; i++) {
-    const int q = tid + TILE_THREADS * i;
-    sidx[i] = (q < 4 * ncell) ? cells[q] - 1 : -1;
-  }
-  const int jend = min(kpt * (slice + 1), (a.kc - cls + 3) / 4);   // fields of this class: k = cls + 4 j
-  for (int j0 = kpt * slice; j0 < jend; j0 += F) {
-    // ---- stage F fields' cells ----
-#pragma unroll
-    for (int f = 0; f < F; f++) {
-      if (j0 + f < jend) {
-        const R* __restrict__ g = a.gi + (size_t)(cls + 4 * (j0 + f)) * a.mi;
-#pragma unroll
-        for (int i = 0; i < NI; i++)
-          if (sidx[i] >= 0) {
-            if (sizeof(R) == 4) cp_async4(&sm[f * CMAX * 4 + tid + TILE_THREADS * i], g + sidx[i]);
-            else cp_async8(&sm[f * CMAX * 4 + tid + TILE_THREADS * i], g + sidx[i]);
-          }
-      }
+  R* gop = a.go + ((size_t)(cls + 4 * jbeg) * a.mo + n0);   // this thread's 4 points in the next field to write
+  u8* lop = a.lo + ((size_t)(cls + 4 * jbeg) * a.mo + n0);
+  const size_t ostep = 4 * (size_t)a.mo;
+  int buf = 0;
+  for (int j0 = jbeg; j0 < jend; j0 += F, buf ^= 1) {
+    if (j0 + F < jend) {
+      stage(buf ^ 1, j0 + F);
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     }
-    cp_async_wait_all();
-    __syncthreads();
+    __syncwarp();
+    const R* __restrict__ sb = sm + buf * BUF;
     // ---- compute ----
-    bool plain = full && (j0 + F <= jend);
-    if (plain) {
-#pragma unroll
-      for (int f = 0; f < F; f++) plain = plain && (a.ibi[cls + 4 * (j0 + f)] == 0);
-    }
+    const bool plain = full && (j0 + F <= jend) && ((maskbits >> (j0 - jbeg)) & ((1u << F) - 1u)) == 0;
     if (plain) {
 #pragma unroll
       for (int f = 0; f < F; f++) {
-        const size_t ob = (size_t)(cls + 4 * (j0 + f)) * a.mo + n0;
-        R o[4];
-        bool ok = true;
+        R G[4], o[4];
 #pragma unroll
         for (int p = 0; p < 4; p++) {
-          const CellRec<R> c = *reinterpret_cast<const CellRec<R>*>(&sm[f * CMAX * 4 + coff[p]]);
-          R G = 0;
+          const CellRec<R> c = *reinterpret_cast<const CellRec<R>*>(&sb[f * CMAX * 4 + coff[p]]);
+          // the reference starts from G=0; 0 + x only changes x = -0, which the quotient maps to +0 again
+          R g = w[p][0] * c.get(0);
 #pragma unroll
-          for (int t = 0; t < 4; t++) G = G + w[p][t] * c.get(t);
-          if (!quot_near1<R>(G, W[p], rW[p], o[p])) { ok = false; o[p] = G; }
+          for (int t = 1; t < 4; t++) g = g + w[p][t] * c.get(t);
+          G[p] = g;
+          o[p] = quot_near1<R>(g, W[p], rW[p]);
         }
-        if (!ok) {
+        const R amax = DM<R>::vmax(DM<R>::vmax(abs_r(G[0]), abs_r(G[1])), DM<R>::vmax(abs_r(G[2]), abs_r(G[3])));
+        const R amin = DM<R>::vmin(DM<R>::vmin(abs_r(G[0]), abs_r(G[1])), DM<R>::vmin(abs_r(G[2]), abs_r(G[3])));
+        if (!(amax < win_hi<R>() && amin >= win_lo<R>())) {
+          // rare: a sum that is zero, tiny, huge or not finite.  Zero is fine as computed; the rest
+          // is outside the exact-residual window and is redone with the IEEE division.
 #pragma unroll
-          for (int p = 0; p < 4; p++) {   // rare: outside the exact-residual window, redo with the IEEE division
-            const CellRec<R> c = *reinterpret_cast<const CellRec<R>*>(&sm[f * CMAX * 4 + coff[p]]);
-            R G = 0;
-#pragma unroll
-            for (int t = 0; t < 4; t++) G = G + w[p][t] * c.get(t);
-            o[p] = G / W[p];
+          for (int p = 0; p < 4; p++) {
+            const R ag = abs_r(G[p]);
+            if (!(ag == (R)0 || (ag < win_hi<R>() && ag >= win_lo<R>()))) o[p] = ((R)0 + G[p]) / W[p];
           }
         }
-        store4<R>(a.go + ob, o[0], o[1], o[2], o[3]);
-        __stcs(reinterpret_cast<unsigned*>(a.lo + ob), 0x01010101u);
+        store4<R>(gop, o[0], o[1], o[2], o[3]);
+        __stcs(reinterpret_cast<unsigned*>(lop), 0x01010101u);
+        gop += ostep; lop += ostep;
       }
     } else {
       // general path, per field: bitmaps, partial stencils, threshold failures, ragged ends
@@ -287,8 +316,7 @@ k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restric
         const int k = cls + 4 * (j0 + f);
         const R* __restrict__ g = a.gi + (size_t)k * a.mi;
         const u8* __restrict__ l = a.li ? a.li + (size_t)k * a.mi : nullptr;
-        const bool masked = a.ibi[k] != 0;
-        const size_t ob = (size_t)k * a.mo;
+        const bool masked = (maskbits >> (j0 + f - jbeg)) & 1u;
         R o[4];
         unsigned lw = 0;
         bool bad = false;
@@ -304,17 +332,18 @@ k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restric
           if (good) lw |= 1u << (8 * p); else bad = true;
         }
         if (n0 >= 0 && n0 + 3 < a.no) {
-          store4<R>(a.go + ob + n0, o[0], o[1], o[2], o[3]);
-          __stcs(reinterpret_cast<unsigned*>(a.lo + ob + n0), lw);
+          store4<R>(gop, o[0], o[1], o[2], o[3]);
+          __stcs(reinterpret_cast<unsigned*>(lop), lw);
         } else {
 #pragma unroll
           for (int p = 0; p < 4; p++)
-            if (n0 + p >= 0 && n0 + p < a.no) { a.go[ob + n0 + p] = o[p]; a.lo[ob + n0 + p] = (u8)((lw >> (8 * p)) & 1u); }
+            if (n0 + p >= 0 && n0 + p < a.no) { gop[p] = o[p]; lop[p] = (u8)((lw >> (8 * p)) & 1u); }
         }
         if (bad) a.flag[k] = 1;
+        gop += ostep; lop += ostep;
       }
     }
-    __syncthreads();
+    __syncwarp();
   }
 }
 
@@ -326,14 +355,26 @@ template <class R> void launch_bilinear_tiles(const Plan<R>& P, const FieldArgs<
   const TileTables& T = P.tiles;
   TileDev D;
   for (int v = 0; v < 4; v++) { D.cid[v] = T.cid[v]; D.ncell[v] = T.ncell[v]; D.cells[v] = T.cells[v]; }
-  D.cstride = T.cstride;
-  constexpr int F = 8, F8 = sizeof(R) == 8 ? 4 : 8;   // fields staged per pass (48 KB of static shared memory at most)
+  D.cstride = T.cstride; D.ntile = T.ntile;
+  constexpr int F = 8, F8 = sizeof(R) == 8 ? 4 : 8;   // fields staged per pass
   const int base_mis = (int)((reinterpret_cast<uintptr_t>(a.go) / sizeof(R)) & 3);
   const int per_class = (a.kc + 3) / 4;
-  const int kpt = std::max(F, std::min(32, ((per_class + F - 1) / F) * F));   // fields of one class per block
-  dim3 grid(4 * nblk(per_class, kpt), T.ntile);
-  if (T.max_cells <= 128) k_bilinear_tiles<R, F, 4><<<grid, TILE_THREADS, 0, st>>>(a, P.nxy, P.wxy, D, base_mis, kpt);
-  else k_bilinear_tiles<R, F8, 8><<<grid, TILE_THREADS, 0, st>>>(a, P.nxy, P.wxy, D, base_mis, kpt);
+  const int kpt = std::max(F, std::min(32, ((per_class + F - 1) / F) * F));   // fields of one class per warp (<= 32: ballot mask)
+  dim3 grid(4 * nblk(per_class, kpt), nblk(T.ntile, TILE_WARPS));
+  const int ni = (4 * T.max_cells + 31) / 32;       // staging copies per lane and field
+#define IPB_TILES_LAUNCH(FF, NN)                                                                                          \
+  {                                                                                                                       \
+    constexpr int SM = TILE_WARPS * 2 * (FF) * (8 * (NN)) * 4 * (int)sizeof(R);                                           \
+    static bool once = false;                                                                                             \
+    if (!once) { IPB_CUDA(cudaFuncSetAttribute(k_bilinear_tiles<R, FF, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); once = true; } \
+    k_bilinear_tiles<R, FF, NN><<<grid, TILE_THREADS, SM, st>>>(a, P.nxy, P.wxy, D, base_mis, kpt);                       \
+  }
+  if (ni <= 2) IPB_TILES_LAUNCH(F, 2)
+  else if (ni <= 3) IPB_TILES_LAUNCH(F, 3)
+  else if (ni <= 4) IPB_TILES_LAUNCH(F, 4)
+  else if (ni <= 6) IPB_TILES_LAUNCH(F8, 6)
+  else IPB_TILES_LAUNCH(F8, 8)
+#undef IPB_TILES_LAUNCH
   g_launches++;
 }
 
