@@ -60,10 +60,11 @@ struct TileTables {
   int ntile = 0, cstride = 0, max_cells = 0;
   u8* cid[4] = {nullptr, nullptr, nullptr, nullptr};     // [ntile*128] cell number of each point inside its tile (0xff: none)
   int* ncell[4] = {nullptr, nullptr, nullptr, nullptr};  // [ntile]
-  int* cells[4] = {nullptr, nullptr, nullptr, nullptr};  // [ntile][cstride][4] 1-based source positions of the cell's taps
+  int* cells[4] = {nullptr, nullptr, nullptr, nullptr};  // [ntile][cstride] staging list: 0-based source position of each entry, sorted (-1 = padding)
+  u8* edst[4] = {nullptr, nullptr, nullptr, nullptr};    // [ntile][cstride] shared-memory slot (cell*4 + tap) of each entry
   size_t bytes = 0;
 };
-struct TileDev { const u8* cid[4]; const int* ncell[4]; const int* cells[4]; int cstride; int ntile; };
+struct TileDev { const u8* cid[4]; const int* ncell[4]; const int* cells[4]; const u8* edst[4]; int cstride; int ntile; };
 
 template <class R> struct Plan {
   std::vector<i64> key;
@@ -99,7 +100,7 @@ template <class R> struct Plan {
     dfree(d_tab_in); dfree(d_tab_out); dfree(rlat); dfree(rlon); dfree(crot); dfree(srot); dfree(x); dfree(y);
     dfree(nxy); dfree(wxy); dfree(cxy); dfree(sxy); dfree(nc); dfree(bn); dfree(bw); dfree(bc); dfree(bs); dfree(d_wb);
     dfree(pole_n); dfree(pole_s); dfree(pclon_n); dfree(pslon_n); dfree(pclon_s); dfree(pslon_s);
-    for (int v = 0; v < 4; v++) { dfree(tiles.cid[v]); dfree(tiles.ncell[v]); dfree(tiles.cells[v]); }
+    for (int v = 0; v < 4; v++) { dfree(tiles.cid[v]); dfree(tiles.ncell[v]); dfree(tiles.cells[v]); dfree(tiles.edst[v]); }
   }
 };
 

@@ -106,11 +106,18 @@ k_tile_index(int variant, int no, int ntile, const int* __restrict__ nxy, u8* __
   reinterpret_cast<unsigned*>(cid)[(size_t)tile * 32 + lane] = packed;
   if (lane == 31) { ncell[tile] = incl; atomicMax(gmax, incl); }
 }
-// pass 2: the cell table itself, [tile][cstride][4] (1-based source positions)
+// pass 2: the staging list of every tile.  Entry e = cell*4 + tap is one 4-byte value to copy per field;
+// entries are sorted by source position so that the 32 copies of one warp instruction fall into a
+// few 32-byte sectors (the copy engine works sector by sector).  esrc = 0-based source position
+// (-1 = padding), edst = shared-memory slot e of the entry.
 static __global__ void __launch_bounds__(TILE_THREADS)
-k_tile_cells(int variant, int no, int ntile, int cstride, const int* __restrict__ nxy, const u8* __restrict__ cid, int* __restrict__ cells) {
-  const int tile = blockIdx.x * TILE_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+k_tile_entries(int variant, int no, int ntile, int estride, const int* __restrict__ nxy, const u8* __restrict__ cid,
+               const int* __restrict__ ncell, int* __restrict__ esrc, u8* __restrict__ edst) {
+  __shared__ int key_all[TILE_WARPS][4 * 64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x * TILE_WARPS + warp;
   if (tile >= ntile) return;
+  int* key = key_all[warp];
   const int nbase = 4 * (tile * 32 + lane) - variant;
   const unsigned packed = reinterpret_cast<const unsigned*>(cid)[(size_t)tile * 32 + lane];
 #pragma unroll
@@ -118,9 +125,20 @@ k_tile_cells(int variant, int no, int ntile, int cstride, const int* __restrict_
     const int n = nbase + p;
     const int c = (packed >> (8 * p)) & 0xff;
     if (c == 0xff || n < 0 || n >= no) continue;
-    int* dst = cells + ((size_t)tile * cstride + c) * 4;   // every point of a cell writes the same four values
 #pragma unroll
-    for (int t = 0; t < 4; t++) dst[t] = nxy[(size_t)t * no + n];
+    for (int t = 0; t < 4; t++) key[c * 4 + t] = nxy[(size_t)t * no + n] - 1;   // every point of a cell writes the same values
+  }
+  __syncwarp();
+  const int ne = 4 * ncell[tile];
+  for (int e = lane; e < estride; e += 32) {
+    if (e >= ne) { esrc[(size_t)tile * estride + e] = -1; edst[(size_t)tile * estride + e] = 0; }
+  }
+  for (int e = lane; e < ne; e += 32) {
+    const int k = key[e];
+    int rank = 0;
+    for (int o = 0; o < ne; o++) { const int ko = key[o]; rank += (ko < k || (ko == k && o < e)) ? 1 : 0; }
+    esrc[(size_t)tile * estride + rank] = k;
+    edst[(size_t)tile * estride + rank] = (u8)e;
   }
 }
 
@@ -151,14 +169,14 @@ template <class R> void build_tile_tables(Plan<R>& P, cudaStream_t st) {
     for (int v = 0; v < 4; v++) { dfree(T.cid[v]); dfree(T.ncell[v]); }
     return;
   }
-  T.cstride = hmax;
+  T.cstride = ((4 * hmax + 31) / 32) * 32;          // staging entries per tile, padded to whole warp instructions
   for (int v = 0; v < 4; v++) {
-    T.cells[v] = dalloc<int>((size_t)ntile * T.cstride * 4);
-    IPB_CUDA(cudaMemsetAsync(T.cells[v], 0, (size_t)ntile * T.cstride * 16, st));
-    k_tile_cells<<<nb, TILE_THREADS, 0, st>>>(v, no, ntile, T.cstride, P.nxy, T.cid[v], T.cells[v]);
+    T.cells[v] = dalloc<int>((size_t)ntile * T.cstride);
+    T.edst[v] = dalloc<u8>((size_t)ntile * T.cstride);
+    k_tile_entries<<<nb, TILE_THREADS, 0, st>>>(v, no, ntile, T.cstride, P.nxy, T.cid[v], T.ncell[v], T.cells[v], T.edst[v]);
     g_launches++;
   }
-  T.bytes = 4 * ((size_t)ntile * TILE_PTS + (size_t)ntile * 4 + (size_t)ntile * T.cstride * 16);
+  T.bytes = 4 * ((size_t)ntile * TILE_PTS + (size_t)ntile * 4 + (size_t)ntile * T.cstride * 5);
   T.ok = true;
 }
 
@@ -168,11 +186,11 @@ template <> struct CellRec<float> { float4 v; __device__ __forceinline__ float g
 template <> struct CellRec<double> { double2 a, b; __device__ __forceinline__ double get(int t) const { return t == 0 ? a.x : t == 1 ? a.y : t == 2 ? b.x : b.y; } };
 
 // predicated 4- / 8-byte asynchronous copy global -> shared (straight-line code, no divergent branch)
-__device__ __forceinline__ void cp_async4_if(bool on, void* smem, const void* gmem) {
-  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p cp.async.ca.shared.global [%0], [%1], 4;\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem), "r"((int)on));
-}
-__device__ __forceinline__ void cp_async8_if(bool on, void* smem, const void* gmem) {
-  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p cp.async.ca.shared.global [%0], [%1], 8;\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem), "r"((int)on));
+template <int BYTES> __device__ __forceinline__ void cp_async_if(bool on, unsigned smem_addr, const void* gmem) {
+  if (BYTES == 4)
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p cp.async.ca.shared.global [%0], [%1], 4;\n}\n" ::"r"(smem_addr), "l"(gmem), "r"((int)on));
+  else
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p cp.async.ca.shared.global [%0], [%1], 8;\n}\n" ::"r"(smem_addr), "l"(gmem), "r"((int)on));
 }
 
 // Correctly rounded g / w for |w - 1| <= 2^-20, given rw = RN(1/w): q0 = g is within a few ulp,
@@ -187,14 +205,25 @@ template <class R> __device__ __forceinline__ R quot_near1(R g, R w, R rw) {
 }
 template <class R> __device__ __forceinline__ R win_lo() { return sizeof(R) == 4 ? (R)6.5e-27f : (R)1e-187; }   // ~2^-87 / 2^-620
 template <class R> __device__ __forceinline__ R win_hi() { return sizeof(R) == 4 ? (R)1.5e26f : (R)1e187; }
-template <class R> __device__ __forceinline__ R abs_r(R x) { return x < 0 ? -x : x; }
+template <class R> __device__ __forceinline__ R abs_r(R x);
+template <> __device__ __forceinline__ float abs_r<float>(float x) { return fabsf(x); }
+template <> __device__ __forceinline__ double abs_r<double>(double x) { return fabs(x); }
+template <class R> __device__ __forceinline__ R max_r(R a, R b);
+template <> __device__ __forceinline__ float max_r<float>(float a, float b) { return fmaxf(a, b); }
+template <> __device__ __forceinline__ double max_r<double>(double a, double b) { return fmax(a, b); }
+template <class R> __device__ __forceinline__ R min_r(R a, R b);
+template <> __device__ __forceinline__ float min_r<float>(float a, float b) { return fminf(a, b); }
+template <> __device__ __forceinline__ double min_r<double>(double a, double b) { return fmin(a, b); }
 
+#ifndef IPB_TILES_MINBLOCKS
+#define IPB_TILES_MINBLOCKS (sizeof(R) == 4 ? 4 : 3)
+#endif
 // F = fields staged per pass, NI = staging copies per lane and field (covers 8*NI cells).
 // Each warp is an independent tile: it stages its own cells into its own shared-memory slice
 // (double buffered: the copies of pass s+1 are in flight while pass s is computed) and never
 // meets a block-wide barrier.
 template <class R, int F, int NI>
-__global__ void __launch_bounds__(TILE_THREADS, sizeof(R) == 4 ? 5 : 3)
+__global__ void __launch_bounds__(TILE_THREADS, IPB_TILES_MINBLOCKS)
 k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restrict__ wxy, TileDev T, int base_mis, int kpt) {
   constexpr int CMAX = 8 * NI;                      // cells a tile may have
   constexpr int BUF = F * CMAX * 4;                 // elements per buffer
@@ -209,26 +238,28 @@ k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restric
   const int jbeg = kpt * slice, jend = min(kpt * (slice + 1), (a.kc - cls + 3) / 4);
   if (jbeg >= jend) return;
   // ---- staging assignment: entry q = cell*4 + tap of this tile's cell table ----
-  const int ncell = T.ncell[variant][tile];
-  const int* __restrict__ cells = T.cells[variant] + (size_t)tile * T.cstride * 4;
+  const int* __restrict__ esrc = T.cells[variant] + (size_t)tile * T.cstride;
+  const u8* __restrict__ edst = T.edst[variant] + (size_t)tile * T.cstride;
   const size_t fstep = 4 * (size_t)a.mi;            // elements between consecutive fields of one class
   const R* gp[NI];                                  // source address of entry i in the next field to stage
+  unsigned sdst[NI];                                // its shared-memory address in buffer 0, field 0
   bool act[NI];
 #pragma unroll
   for (int i = 0; i < NI; i++) {
     const int q = lane + 32 * i;
-    act[i] = q < 4 * ncell;
-    gp[i] = a.gi + (size_t)(cls + 4 * jbeg) * a.mi + (act[i] ? cells[q] - 1 : 0);
+    const int src = q < T.cstride ? esrc[q] : -1;
+    act[i] = src >= 0;
+    gp[i] = a.gi + (size_t)(cls + 4 * jbeg) * a.mi + (act[i] ? src : 0);
+    sdst[i] = (unsigned)__cvta_generic_to_shared(sm + (act[i] ? (int)edst[q] : 0));
   }
   auto stage = [&](int buf, int j0) {
-    R* dst = sm + buf * BUF + lane;
+    const unsigned boff = (unsigned)(buf * BUF * sizeof(R));
     if (j0 + F <= jend) {          // whole pass: straight-line copies
 #pragma unroll
       for (int f = 0; f < F; f++) {
 #pragma unroll
         for (int i = 0; i < NI; i++) {
-          if (sizeof(R) == 4) cp_async4_if(act[i], dst + f * CMAX * 4 + 32 * i, gp[i]);
-          else cp_async8_if(act[i], dst + f * CMAX * 4 + 32 * i, gp[i]);
+          cp_async_if<sizeof(R)>(act[i], sdst[i] + boff + (unsigned)(f * CMAX * 4 * sizeof(R)), gp[i]);
           gp[i] += fstep;
         }
       }
@@ -236,8 +267,7 @@ k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restric
       for (int f = 0; j0 + f < jend; f++) {
 #pragma unroll
         for (int i = 0; i < NI; i++) {
-          if (sizeof(R) == 4) cp_async4_if(act[i], dst + f * CMAX * 4 + 32 * i, gp[i]);
-          else cp_async8_if(act[i], dst + f * CMAX * 4 + 32 * i, gp[i]);
+          cp_async_if<sizeof(R)>(act[i], sdst[i] + boff + (unsigned)(f * CMAX * 4 * sizeof(R)), gp[i]);
           gp[i] += fstep;
         }
       }
@@ -245,8 +275,9 @@ k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restric
     asm volatile("cp.async.commit_group;\n" ::: "memory");
   };
   stage(0, jbeg);
-  // bit j-jbeg set: field j of this warp carries a bitmap (kpt <= 32)
-  const unsigned maskbits = __ballot_sync(0xffffffffu, (jbeg + lane < jend) && a.ibi[cls + 4 * (jbeg + lane)] != 0);
+  // bit b set: field j = jm0 + b of this warp carries a bitmap; refreshed every 32 fields
+  unsigned maskbits = __ballot_sync(0xffffffffu, (jbeg + lane < jend) && a.ibi[cls + 4 * (jbeg + lane)] != 0);
+  int jm0 = jbeg;
   // ---- per-thread plan data: weights, weight sums, cell numbers ----
   R w[4][4], W[4], rW[4];
   int coff[4];
@@ -279,8 +310,12 @@ k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restric
     }
     __syncwarp();
     const R* __restrict__ sb = sm + buf * BUF;
+    if (j0 - jm0 >= 32) {
+      jm0 = j0;
+      maskbits = __ballot_sync(0xffffffffu, (j0 + lane < jend) && a.ibi[cls + 4 * (j0 + lane)] != 0);
+    }
     // ---- compute ----
-    const bool plain = full && (j0 + F <= jend) && ((maskbits >> (j0 - jbeg)) & ((1u << F) - 1u)) == 0;
+    const bool plain = full && (j0 + F <= jend) && ((maskbits >> (j0 - jm0)) & ((1u << F) - 1u)) == 0;
     if (plain) {
 #pragma unroll
       for (int f = 0; f < F; f++) {
@@ -295,14 +330,14 @@ k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restric
           G[p] = g;
           o[p] = quot_near1<R>(g, W[p], rW[p]);
         }
-        const R amax = DM<R>::vmax(DM<R>::vmax(abs_r(G[0]), abs_r(G[1])), DM<R>::vmax(abs_r(G[2]), abs_r(G[3])));
-        const R amin = DM<R>::vmin(DM<R>::vmin(abs_r(G[0]), abs_r(G[1])), DM<R>::vmin(abs_r(G[2]), abs_r(G[3])));
+        const R amax = max_r<R>(max_r<R>(abs_r<R>(G[0]), abs_r<R>(G[1])), max_r<R>(abs_r<R>(G[2]), abs_r<R>(G[3])));
+        const R amin = min_r<R>(min_r<R>(abs_r<R>(G[0]), abs_r<R>(G[1])), min_r<R>(abs_r<R>(G[2]), abs_r<R>(G[3])));
         if (!(amax < win_hi<R>() && amin >= win_lo<R>())) {
           // rare: a sum that is zero, tiny, huge or not finite.  Zero is fine as computed; the rest
           // is outside the exact-residual window and is redone with the IEEE division.
 #pragma unroll
           for (int p = 0; p < 4; p++) {
-            const R ag = abs_r(G[p]);
+            const R ag = abs_r<R>(G[p]);
             if (!(ag == (R)0 || (ag < win_hi<R>() && ag >= win_lo<R>()))) o[p] = ((R)0 + G[p]) / W[p];
           }
         }
@@ -316,7 +351,7 @@ k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restric
         const int k = cls + 4 * (j0 + f);
         const R* __restrict__ g = a.gi + (size_t)k * a.mi;
         const u8* __restrict__ l = a.li ? a.li + (size_t)k * a.mi : nullptr;
-        const bool masked = (maskbits >> (j0 + f - jbeg)) & 1u;
+        const bool masked = (maskbits >> (j0 + f - jm0)) & 1u;
         R o[4];
         unsigned lw = 0;
         bool bad = false;
@@ -354,12 +389,13 @@ template <class R> bool tiles_ok(const Plan<R>& P, const FieldArgs<R>& a) {
 template <class R> void launch_bilinear_tiles(const Plan<R>& P, const FieldArgs<R>& a, cudaStream_t st) {
   const TileTables& T = P.tiles;
   TileDev D;
-  for (int v = 0; v < 4; v++) { D.cid[v] = T.cid[v]; D.ncell[v] = T.ncell[v]; D.cells[v] = T.cells[v]; }
+  for (int v = 0; v < 4; v++) { D.cid[v] = T.cid[v]; D.ncell[v] = T.ncell[v]; D.cells[v] = T.cells[v]; D.edst[v] = T.edst[v]; }
   D.cstride = T.cstride; D.ntile = T.ntile;
   constexpr int F = 8, F8 = sizeof(R) == 8 ? 4 : 8;   // fields staged per pass
   const int base_mis = (int)((reinterpret_cast<uintptr_t>(a.go) / sizeof(R)) & 3);
   const int per_class = (a.kc + 3) / 4;
-  const int kpt = std::max(F, std::min(32, ((per_class + F - 1) / F) * F));   // fields of one class per warp (<= 32: ballot mask)
+  static const int kpt_env = getenv("IPB_KPT") ? atoi(getenv("IPB_KPT")) : 64;
+  const int kpt = std::max(32, std::min(kpt_env, ((per_class + 31) / 32) * 32));   // fields of one class per warp (multiple of 32)
   dim3 grid(4 * nblk(per_class, kpt), nblk(T.ntile, TILE_WARPS));
   const int ni = (4 * T.max_cells + 31) / 32;       // staging copies per lane and field
 #define IPB_TILES_LAUNCH(FF, NN)                                                                                          \
