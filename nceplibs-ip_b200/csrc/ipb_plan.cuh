@@ -93,6 +93,7 @@ template <class R> struct Plan {
   // 1-based range of input-field positions any tap refers to (host calls copy only this window)
   int src_lo = 1, src_hi = 0;
   TileTables tiles;
+  R *wq = nullptr, *ws2 = nullptr;   // staged bilinear kernel: weights per point [no][4], (sum, 1/sum) [no][2]
   size_t bytes = 0;
   double build_ms = 0;
 
@@ -101,6 +102,7 @@ template <class R> struct Plan {
     dfree(nxy); dfree(wxy); dfree(cxy); dfree(sxy); dfree(nc); dfree(bn); dfree(bw); dfree(bc); dfree(bs); dfree(d_wb);
     dfree(pole_n); dfree(pole_s); dfree(pclon_n); dfree(pslon_n); dfree(pclon_s); dfree(pslon_s);
     for (int v = 0; v < 4; v++) { dfree(tiles.cid[v]); dfree(tiles.ncell[v]); dfree(tiles.cells[v]); dfree(tiles.edst[v]); }
+    dfree(wq); dfree(ws2);
   }
 };
 

@@ -142,6 +142,19 @@ k_tile_entries(int variant, int no, int ntile, int estride, const int* __restric
   }
 }
 
+// Per-point weight record of the staged kernel: the four tap weights contiguous (one 16/32-byte load per
+// point instead of four scattered ones), and the weight sum with its correctly rounded reciprocal.
+template <class R>
+__global__ void k_tile_weights(int no, const R* __restrict__ wxy, R* __restrict__ wq, R* __restrict__ ws2) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= no) return;
+  R s = 0;
+#pragma unroll
+  for (int t = 0; t < 4; t++) { const R w = wxy[(size_t)t * no + n]; wq[(size_t)n * 4 + t] = w; s = s + w; }   // reference order (1,1),(2,1),(1,2),(2,2)
+  ws2[(size_t)n * 2] = s;
+  ws2[(size_t)n * 2 + 1] = (R)1 / s;
+}
+
 constexpr int TILE_MAX_CELLS = 64;   // staging covers 8*NI cells per tile, NI <= 8
 
 template <class R> void build_tile_tables(Plan<R>& P, cudaStream_t st) {
@@ -176,7 +189,11 @@ template <class R> void build_tile_tables(Plan<R>& P, cudaStream_t st) {
     k_tile_entries<<<nb, TILE_THREADS, 0, st>>>(v, no, ntile, T.cstride, P.nxy, T.cid[v], T.ncell[v], T.cells[v], T.edst[v]);
     g_launches++;
   }
-  T.bytes = 4 * ((size_t)ntile * TILE_PTS + (size_t)ntile * 4 + (size_t)ntile * T.cstride * 5);
+  P.wq = dalloc<R>((size_t)no * 4);
+  P.ws2 = dalloc<R>((size_t)no * 2);
+  k_tile_weights<R><<<nblk(no, 256), 256, 0, st>>>(no, P.wxy, P.wq, P.ws2);
+  g_launches++;
+  T.bytes = 4 * ((size_t)ntile * TILE_PTS + (size_t)ntile * 4 + (size_t)ntile * T.cstride * 5) + (size_t)no * 6 * sizeof(R);
   T.ok = true;
 }
 
@@ -224,7 +241,7 @@ template <> __device__ __forceinline__ double min_r<double>(double a, double b) 
 // meets a block-wide barrier.
 template <class R, int F, int NI>
 __global__ void __launch_bounds__(TILE_THREADS, IPB_TILES_MINBLOCKS)
-k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restrict__ wxy, TileDev T, int base_mis, int kpt) {
+k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restrict__ wq, const R* __restrict__ ws2, TileDev T, int base_mis, int kpt) {
   constexpr int CMAX = 8 * NI;                      // cells a tile may have
   constexpr int BUF = F * CMAX * 4;                 // elements per buffer
   extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -254,15 +271,15 @@ k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restric
   }
   auto stage = [&](int buf, int j0) {
     const unsigned boff = (unsigned)(buf * BUF * sizeof(R));
-    if (j0 + F <= jend) {          // whole pass: straight-line copies
+    if (j0 + F <= jend) {          // whole pass: straight-line copies, addresses formed in temporaries
 #pragma unroll
       for (int f = 0; f < F; f++) {
 #pragma unroll
-        for (int i = 0; i < NI; i++) {
-          cp_async_if<sizeof(R)>(act[i], sdst[i] + boff + (unsigned)(f * CMAX * 4 * sizeof(R)), gp[i]);
-          gp[i] += fstep;
-        }
+        for (int i = 0; i < NI; i++)
+          cp_async_if<sizeof(R)>(act[i], sdst[i] + boff + (unsigned)(f * CMAX * 4 * sizeof(R)), gp[i] + (size_t)f * fstep);
       }
+#pragma unroll
+      for (int i = 0; i < NI; i++) gp[i] += (size_t)F * fstep;
     } else {                       // ragged last pass
       for (int f = 0; j0 + f < jend; f++) {
 #pragma unroll
@@ -288,15 +305,23 @@ k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restric
     const int n = n0 + p;
     const bool in = n >= 0 && n < a.no;
     const int c = (packed >> (8 * p)) & 0xff;
-    R ws = 0;
-#pragma unroll
-    for (int t = 0; t < 4; t++) { w[p][t] = in ? wxy[(size_t)t * a.no + n] : (R)0; ws = ws + w[p][t]; }
-    W[p] = ws;
-    rW[p] = (R)1 / ws;
+    const size_t nn = in ? (size_t)n : 0;
+    if (sizeof(R) == 4) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(wq) + nn);
+      const float2 s2 = __ldg(reinterpret_cast<const float2*>(ws2) + nn);
+      w[p][0] = (R)q.x; w[p][1] = (R)q.y; w[p][2] = (R)q.z; w[p][3] = (R)q.w; W[p] = (R)s2.x; rW[p] = (R)s2.y;
+    } else {
+      const double2 q0 = __ldg(reinterpret_cast<const double2*>(wq) + 2 * nn), q1 = __ldg(reinterpret_cast<const double2*>(wq) + 2 * nn + 1);
+      const double2 s2 = __ldg(reinterpret_cast<const double2*>(ws2) + nn);
+      w[p][0] = (R)q0.x; w[p][1] = (R)q0.y; w[p][2] = (R)q1.x; w[p][3] = (R)q1.y; W[p] = (R)s2.x; rW[p] = (R)s2.y;
+    }
+    const R ws = W[p];
     coff[p] = c * 4;
     const R dev = ws - (R)1;
     full = full && in && c != 0xff && ws >= a.pmp && dev <= (R)9.5e-7 && dev >= (R)-9.5e-7;
   }
+  const bool same1a = coff[1] == coff[0], same2a = coff[2] == coff[0];
+  const bool own1 = !same1a && coff[1] != coff[3], own2 = !same2a && coff[2] != coff[3];
   R* gop = a.go + ((size_t)(cls + 4 * jbeg) * a.mo + n0);   // this thread's 4 points in the next field to write
   u8* lop = a.lo + ((size_t)(cls + 4 * jbeg) * a.mo + n0);
   const size_t ostep = 4 * (size_t)a.mo;
@@ -320,9 +345,20 @@ k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restric
 #pragma unroll
       for (int f = 0; f < F; f++) {
         R G[4], o[4];
+        // the 4 consecutive points of a thread usually lie in one or two source cells: the records of
+        // the first and the last point are loaded, the middle points reuse them (a third load only
+        // where a middle point sits in a cell of its own) — shared-memory bandwidth is what bounds
+        // this loop, not instruction issue
+        CellRec<R> rec[4];
+        rec[0] = *reinterpret_cast<const CellRec<R>*>(&sb[f * CMAX * 4 + coff[0]]);
+        rec[3] = *reinterpret_cast<const CellRec<R>*>(&sb[f * CMAX * 4 + coff[3]]);
+        rec[1] = same1a ? rec[0] : rec[3];
+        rec[2] = same2a ? rec[0] : rec[3];
+        if (own1) rec[1] = *reinterpret_cast<const CellRec<R>*>(&sb[f * CMAX * 4 + coff[1]]);
+        if (own2) rec[2] = *reinterpret_cast<const CellRec<R>*>(&sb[f * CMAX * 4 + coff[2]]);
 #pragma unroll
         for (int p = 0; p < 4; p++) {
-          const CellRec<R> c = *reinterpret_cast<const CellRec<R>*>(&sb[f * CMAX * 4 + coff[p]]);
+          const CellRec<R>& c = rec[p];
           // the reference starts from G=0; 0 + x only changes x = -0, which the quotient maps to +0 again
           R g = w[p][0] * c.get(0);
 #pragma unroll
@@ -403,7 +439,7 @@ template <class R> void launch_bilinear_tiles(const Plan<R>& P, const FieldArgs<
     constexpr int SM = TILE_WARPS * 2 * (FF) * (8 * (NN)) * 4 * (int)sizeof(R);                                           \
     static bool once = false;                                                                                             \
     if (!once) { IPB_CUDA(cudaFuncSetAttribute(k_bilinear_tiles<R, FF, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); once = true; } \
-    k_bilinear_tiles<R, FF, NN><<<grid, TILE_THREADS, SM, st>>>(a, P.nxy, P.wxy, D, base_mis, kpt);                       \
+    k_bilinear_tiles<R, FF, NN><<<grid, TILE_THREADS, SM, st>>>(a, P.nxy, P.wq, P.ws2, D, base_mis, kpt);                       \
   }
   if (ni <= 2) IPB_TILES_LAUNCH(F, 2)
   else if (ni <= 3) IPB_TILES_LAUNCH(F, 3)
