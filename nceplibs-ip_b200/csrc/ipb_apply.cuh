@@ -70,12 +70,57 @@ k_apply_stencil(FieldArgs<R> a, GridP<R> gin, int kpb, const int* __restrict__ n
   const int cls = (NT == 4) ? nc[n] : 1;
   const R cr = VEC ? crot[n] : (R)1, sr = VEC ? srot[n] : (R)0;
   const int k0 = blockIdx.y * kpb, k1 = min(k0 + kpb, a.kc);
+  // complete stencil: every tap present (bicubic: the true 4x4 case).  Without a bitmap the tap set and
+  // the weight sum are then the same for every field, and the field loop is straight-line code.
+  bool complete = cls == 1;
+  R Wall = 0;
+#pragma unroll
+  for (int t = 0; t < T2; t++) { complete = complete && idx[t] > 0; Wall = Wall + w[t]; }
+  complete = complete && Wall >= a.pmp;
   for (int k = k0; k < k1; k++) {
     const R* __restrict__ g = a.gi + (size_t)k * a.mi;
     const R* __restrict__ gv = VEC ? a.vi + (size_t)k * a.mi : nullptr;
     const bool masked = a.ibi[k] != 0;
     const u8* __restrict__ l = a.li ? a.li + (size_t)k * a.mi : nullptr;
     const size_t oa = (size_t)k * a.mo + n;
+    if (complete && !masked) {   // complete also means the weight sum passes the threshold
+      R G = 0, V = 0;
+      R gmin = DM<R>::huge(), gmax = -DM<R>::huge(), vmin = DM<R>::huge(), vmax = -DM<R>::huge();
+      R tv[T2], tu[VEC ? T2 : 1];
+#pragma unroll
+      for (int t = 0; t < T2; t++) { tv[t] = __ldg(g + (idx[t] - 1)); if (VEC) tu[t] = __ldg(gv + (idx[t] - 1)); }
+#pragma unroll
+      for (int t = 0; t < T2; t++) {
+        if (!VEC) {
+          G = G + w[t] * tv[t];
+          if (NT == 4 && a.mcon > 0) { gmin = DM<R>::vmin(gmin, tv[t]); gmax = DM<R>::vmax(gmax, tv[t]); }
+        } else {
+          const R u = tv[t], v = tu[t];
+          const R ur = c[t] * u - s[t] * v;
+          const R vr = s[t] * u + c[t] * v;
+          G = G + w[t] * ur;
+          V = V + w[t] * vr;
+          if (NT == 4 && a.mcon > 0) {
+            gmin = DM<R>::vmin(gmin, ur); gmax = DM<R>::vmax(gmax, ur);
+            vmin = DM<R>::vmin(vmin, vr); vmax = DM<R>::vmax(vmax, vr);
+          }
+        }
+      }
+      R og, ov = 0;
+      if (!VEC) {
+        og = G / Wall;
+        if (NT == 4 && a.mcon > 0) og = DM<R>::vmin(DM<R>::vmax(og, gmin), gmax);
+      } else {
+        const R ur = cr * G - sr * V;
+        const R vr = sr * G + cr * V;
+        og = ur / Wall; ov = vr / Wall;
+        if (NT == 4 && a.mcon > 0) { og = DM<R>::vmin(DM<R>::vmax(og, gmin), gmax); ov = DM<R>::vmin(DM<R>::vmax(ov, vmin), vmax); }
+      }
+      __stcs(a.go + oa, og);
+      if (VEC) __stcs(a.vo + oa, ov);
+      __stcs(a.lo + oa, (u8)1);
+      continue;
+    }
     R G = 0, V = 0, W = 0;
     R gmin = DM<R>::huge(), gmax = -DM<R>::huge(), vmin = DM<R>::huge(), vmax = -DM<R>::huge();
     bool good = false;

@@ -55,7 +55,7 @@ void launch_apply(const Plan<R>& P, bool vec, FieldArgs<R> a, cudaStream_t st) {
   if (method == M_BILINEAR || method == M_BICUBIC) {
     if (method == M_BILINEAR && !vec && tiles_ok(P, a)) { launch_bilinear_tiles(P, a, st); return; }
     if (method == M_BILINEAR && !vec && fast_bilinear_ok(P, a)) { launch_fast_bilinear(P, a, st); return; }
-    const int kpb = std::max(1, std::min(a.kc, 16));
+    const int kpb = std::max(1, std::min(a.kc, 64));   // fields per thread: the plan entry is re-read once per kpb fields
     dim3 grid(nblk(no, 128), nblk(a.kc, kpb));
     if (method == M_BILINEAR) {
       if (vec) k_apply_stencil<R, 2, true><<<grid, 128, 0, st>>>(a, gi, kpb, P.nxy, P.wxy, P.cxy, P.sxy, P.nc, P.x, P.y, P.crot, P.srot);
@@ -66,13 +66,14 @@ void launch_apply(const Plan<R>& P, bool vec, FieldArgs<R> a, cudaStream_t st) {
     }
     g_launches++;
   } else if (method == M_NEIGHBOR) {
+    if (!vec && fast_neighbor_ok(P, a)) { launch_fast_neighbor(P, a, st); return; }
     const int kpb = std::max(1, std::min(a.kc, 32));
     dim3 grid(nblk(no, 256), nblk(a.kc, kpb));
     if (vec) k_apply_neighbor<R, true><<<grid, 256, 0, st>>>(a, gi, kpb, P.nxy, P.cxy, P.sxy, P.x, P.y, P.rlat, P.rlon, P.crot, P.srot);
     else k_apply_neighbor<R, false><<<grid, 256, 0, st>>>(a, gi, kpb, P.nxy, nullptr, nullptr, P.x, P.y, P.rlat, P.rlon, nullptr, nullptr);
     g_launches++;
   } else {
-    constexpr int KF = 8;
+    constexpr int KF = 8;   // fields per thread: the sub-sample taps are re-read once per KF fields
     dim3 grid(nblk(no, 128), nblk(a.kc, KF));
     const int ns = P.bo.nsamp;
     if (method == M_BUDGET) {

@@ -168,4 +168,57 @@ template <class R> void launch_fast_bilinear(const Plan<R>& P, const FieldArgs<R
   g_launches++;
 }
 
+// ---- neighbor, scalar (ipolates ip=2, neighbor_interp_mod.F90:213-263) --------------------------------
+// One output point per lane, so that the 32 gathers of a warp instruction fall on neighbouring source
+// points (a few 32-byte sectors) whatever the resolution ratio of the two grids; go is stored as one
+// coalesced 128-byte line per warp and field, lo as 32 bytes.  A thread walks a slice of the field
+// batch with its source position in a register; four fields are in flight at a time.
+template <class R>
+__global__ void __launch_bounds__(256)
+k_neighbor_lane(FieldArgs<R> a, const int* __restrict__ nxy, int kpb) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= a.no) return;
+  const int p0 = nxy[n];
+  const int k0 = blockIdx.y * kpb, k1 = min(k0 + kpb, a.kc);
+  const R* __restrict__ g = a.gi + (size_t)k0 * a.mi + (p0 > 0 ? p0 - 1 : 0);
+  R* go = a.go + (size_t)k0 * a.mo + n;
+  u8* lo = a.lo + (size_t)k0 * a.mo + n;
+  if (a.li == nullptr) {   // no bitmap anywhere in this call: lo depends on the point only
+    const u8 ok = p0 > 0 ? 1 : 0;
+    int k = k0;
+    for (; k + 4 <= k1; k += 4) {
+      R v[4];
+#pragma unroll
+      for (int f = 0; f < 4; f++) v[f] = ok ? __ldg(g + (size_t)f * a.mi) : (R)0;
+#pragma unroll
+      for (int f = 0; f < 4; f++) { __stcs(go + (size_t)f * a.mo, v[f]); __stcs(lo + (size_t)f * a.mo, ok); }
+      g += 4 * (size_t)a.mi; go += 4 * (size_t)a.mo; lo += 4 * (size_t)a.mo;
+    }
+    for (; k < k1; k++) {
+      __stcs(go, ok ? __ldg(g) : (R)0); __stcs(lo, ok);
+      g += a.mi; go += a.mo; lo += a.mo;
+    }
+    if (!ok) for (int kk = k0; kk < k1; kk++) a.flag[kk] = 1;
+    return;
+  }
+  const u8* __restrict__ l = a.li + (size_t)k0 * a.mi + (p0 > 0 ? p0 - 1 : 0);
+  for (int k = k0; k < k1; k++) {
+    const bool ok = p0 > 0 && (a.ibi[k] == 0 || *l);
+    __stcs(go, ok ? __ldg(g) : (R)0); __stcs(lo, (u8)(ok ? 1 : 0));
+    if (!ok) a.flag[k] = 1;
+    g += a.mi; l += a.mi; go += a.mo; lo += a.mo;
+  }
+}
+
+template <class R> bool fast_neighbor_ok(const Plan<R>& P, const FieldArgs<R>& a) {
+  return P.method == M_NEIGHBOR && !P.vec && a.mspiral <= 1 && P.no > 0;
+}
+
+template <class R> void launch_fast_neighbor(const Plan<R>& P, const FieldArgs<R>& a, cudaStream_t st) {
+  const int kpb = std::max(1, std::min(a.kc, 256));
+  dim3 grid(nblk(a.no, 256), nblk(a.kc, kpb));
+  k_neighbor_lane<R><<<grid, 256, 0, st>>>(a, P.nxy, kpb);
+  g_launches++;
+}
+
 }  // namespace ipb
