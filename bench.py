@@ -143,6 +143,12 @@ def cpu_arm(wl, sample_km=None, target_s=12.0, steps=None, warmup=1):
     kind = wl["kind"]
     # the plain-glibc flavour: the libm a gfortran build of the reference links on this host (oracle/ip_oracle_libm.hpp)
     o = oracle(kind, "glibc")
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which is not what is wanted here)
+    try:
+        nthr = len(os.sched_getaffinity(0))
+    except AttributeError:
+        nthr = os.cpu_count() or 1
+    o.lib.oracle_set_num_threads(C.c_int(int(os.environ.get("IPB_CPU_THREADS", nthr))))
     o.lib.oracle_num_threads.restype = C.c_int
     cores = int(o.lib.oracle_num_threads())
     R, I = o.R, o.I
@@ -227,10 +233,22 @@ def run_gpu(args, wl):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
+    torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
+        # NCCL may print a version banner on stdout while the communicator is created; stdout carries exactly one
+        # JSON line, so route fd 1 to stderr until the first collective is through
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     dev = torch.device("cuda", local)
     pkg = _pkg()
     kind = wl["kind"]

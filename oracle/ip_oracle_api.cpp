@@ -129,6 +129,13 @@ ORACLE_KIND(4, float, int32_t)
 ORACLE_KIND(d, double, int32_t)
 ORACLE_KIND(8, double, int64_t)
 
+// launchers such as torchrun export OMP_NUM_THREADS=1; the timing harness sets the thread count explicitly
+extern "C" void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#endif
+}
+
 extern "C" int oracle_num_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();
