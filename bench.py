@@ -364,7 +364,12 @@ def run_gpu(args, wl):
     plan_bytes = L.ipgpu_plan_bytes()
     touched = args_touched(wl)
     Rb = np.dtype(R).itemsize
-    bpu = algorithmic_bytes(wl, Rb, no, touched, plan_bytes / max(no, 1), km)
+    plan_pp = plan_bytes / max(no, 1)
+    if wl["ip"] == 3 and kind != "4":
+        # budget, binary64 kinds: the apply kernel reads the collapsed taps (9 positions + 9 weights + the weight sum per
+        # point, csrc/ipb_budget.cuh), not the 1200 B/point sub-sample plan it was derived from
+        plan_pp = 9 * (4 + Rb) + Rb
+    bpu = algorithmic_bytes(wl, Rb, no, touched, plan_pp, km)
     k_ms = sum(apply_ms) / len(apply_ms)
     peaks = {}
     try:

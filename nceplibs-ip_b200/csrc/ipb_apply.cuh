@@ -49,15 +49,31 @@ __device__ int spiral_find(const GridP<R>& gin, R x, R y, int first, int mspiral
   return 0;
 }
 
+// Output point of a thread in a block that covers a 32 x ROWS patch of the output grid (rows of `rowlen`
+// consecutive points, one warp per row): the warps of a block gather from the same few source rows, so the
+// sectors one warp pulls into L1 are hits for the others.  Returns -1 outside the grid.
+template <int ROWS> __device__ __forceinline__ int patch_point(int rowlen, int no) {
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+  const long long n = (long long)(blockIdx.y * ROWS + (threadIdx.x >> 5)) * rowlen + col;
+  return (col < rowlen && n < no) ? (int)n : -1;
+}
+inline dim3 patch_grid(int rowlen, int no, int rows) { return dim3(nblk(rowlen, 32), nblk(nblk(no, rowlen), rows)); }
+// Row length of a grid's own point enumeration (gdswzd iopt=0); 256 (plain linear blocks) for station points.
+template <class R> inline int patch_rowlen(const GridP<R>& g, int no) {
+  if (g.type == P_STATION || g.im <= 0 || g.jm <= 0) return 256;
+  const int r = g.nscan == 0 ? g.im : g.jm;
+  return (r > 0 && r <= no) ? r : 256;
+}
+
 // ---- bilinear (NT=2) / bicubic (NT=4), scalar and vector -------------------------------------------
 // KPB = fields walked by one thread (grid.y covers ceil(kc/KPB)).
 template <class R, int NT, bool VEC>
 __global__ void __launch_bounds__(128)
 k_apply_stencil(FieldArgs<R> a, GridP<R> gin, int kpb, const int* __restrict__ nxy, const R* __restrict__ wxy,
                 const R* __restrict__ cxy, const R* __restrict__ sxy, const u8* __restrict__ nc,
-                const R* __restrict__ xs, const R* __restrict__ ys, const R* __restrict__ crot, const R* __restrict__ srot) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= a.no) return;
+                const R* __restrict__ xs, const R* __restrict__ ys, const R* __restrict__ crot, const R* __restrict__ srot, int rowlen) {
+  const int n = patch_point<4>(rowlen, a.no);
+  if (n < 0) return;
   constexpr int T2 = NT * NT;
   int idx[T2];
   R w[T2], c[VEC ? T2 : 1], s[VEC ? T2 : 1];
@@ -69,7 +85,7 @@ k_apply_stencil(FieldArgs<R> a, GridP<R> gin, int kpb, const int* __restrict__ n
   }
   const int cls = (NT == 4) ? nc[n] : 1;
   const R cr = VEC ? crot[n] : (R)1, sr = VEC ? srot[n] : (R)0;
-  const int k0 = blockIdx.y * kpb, k1 = min(k0 + kpb, a.kc);
+  const int k0 = blockIdx.z * kpb, k1 = min(k0 + kpb, a.kc);
   // complete stencil: every tap present (bicubic: the true 4x4 case).  Without a bitmap the tap set and
   // the weight sum are then the same for every field, and the field loop is straight-line code.
   bool complete = cls == 1;
@@ -339,6 +355,99 @@ k_apply_budget(FieldArgs<R> a, GridP<R> gin, int nsamp, const int* __restrict__ 
     a.go[oa] = og;
     if (VEC) a.vo[oa] = ov;
     a.lo[oa] = good ? 1 : 0;
+    if (!good) a.flag[k] = 1;
+  }
+}
+
+// if (on) { a += x; b += y; } as two predicated adds (the compiler's own choice is an unconditional add plus
+// register selects, four more instructions per tap in binary64)
+template <class R> __device__ __forceinline__ void add2_if(unsigned on, R& a, R x, R& b, R y);
+template <> __device__ __forceinline__ void add2_if<double>(unsigned on, double& a, double x, double& b, double y) {
+  asm("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p add.rn.f64 %0, %0, %3;\n @p add.rn.f64 %1, %1, %4;\n}\n" : "+d"(a), "+d"(b) : "r"(on), "d"(x), "d"(y));
+}
+template <> __device__ __forceinline__ void add2_if<float>(unsigned on, float& a, float x, float& b, float y) {
+  asm("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p add.rn.f32 %0, %0, %3;\n @p add.rn.f32 %1, %1, %4;\n}\n" : "+f"(a), "+f"(b) : "r"(on), "f"(x), "f"(y));
+}
+
+// ---- budget, scalar, without spiral search: the batched kernel ------------------------------------------
+// budget_interp_mod.F90:252-344.  The sub-sample plan is large (25 samples x 4 taps x (index + weight) =
+// 1200 bytes per output point in the _d kind) and does not fit L2, so what bounds this method is how often
+// the plan is streamed.  A block owns 32 consecutive output points (one per lane) and 8 x KF fields (warp w
+// owns fields w*KF .. w*KF+KF-1): every chunk of samples is copied once into shared memory — coalesced, the
+// plan is tap-major — and used by all eight warps, so the plan crosses HBM once per 64 fields instead of once
+// per 8.  Accumulation order and association are the reference's: per sample either the 4-tap sum times the
+// sample weight (field without bitmap) or tap by tap with the product wb*w formed first (field with bitmap).
+template <class R, int KF>
+__global__ void __launch_bounds__(256)
+k_budget_scalar(FieldArgs<R> a, int nsamp, const int* __restrict__ bn, const R* __restrict__ bw, const R* __restrict__ wbs) {
+  constexpr int SCH = 16;                              // samples per shared-memory chunk
+  __shared__ int s_idx[SCH * 4 * 32];
+  __shared__ R s_w[SCH * 4 * 32];
+  __shared__ R s_wb[SCH];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + lane;
+  const bool live = n < a.no;
+  const int k0 = (blockIdx.y * 8 + warp) * KF;         // first field of this warp
+  R acc[KF], wo[KF];
+  unsigned maskbits = 0;
+#pragma unroll
+  for (int f = 0; f < KF; f++) {
+    acc[f] = 0; wo[f] = 0;
+    if (k0 + f < a.kc && a.ibi[k0 + f] != 0) maskbits |= 1u << f;
+  }
+  R wo_plain = 0;                                      // weight sum of the fields without a bitmap (the same for all of them)
+  for (int s0 = 0; s0 < nsamp; s0 += SCH) {
+    const int ns = min(SCH, nsamp - s0);
+    __syncthreads();
+    for (int r = warp; r < ns * 4; r += 8) {           // row r = (sample, tap): 32 consecutive points
+      const size_t src = (size_t)(s0 * 4 + r) * a.no + n;
+      s_idx[r * 32 + lane] = live ? bn[src] : 0;
+      s_w[r * 32 + lane] = live ? bw[src] : (R)0;
+    }
+    if (threadIdx.x < ns) s_wb[threadIdx.x] = wbs[s0 + threadIdx.x];
+    __syncthreads();
+    if (k0 >= a.kc) continue;                          // a warp without fields only helps with the copies
+    for (int s = 0; s < ns; s++) {
+      const int i0 = s_idx[(s * 4 + 0) * 32 + lane];
+      if (i0 <= 0) continue;                           // sample outside the input grid for this point
+      const int i1 = s_idx[(s * 4 + 1) * 32 + lane], i2 = s_idx[(s * 4 + 2) * 32 + lane], i3 = s_idx[(s * 4 + 3) * 32 + lane];
+      const R w0 = s_w[(s * 4 + 0) * 32 + lane], w1 = s_w[(s * 4 + 1) * 32 + lane];
+      const R w2 = s_w[(s * 4 + 2) * 32 + lane], w3 = s_w[(s * 4 + 3) * 32 + lane];
+      const R wb = s_wb[s];
+      const R b0 = wb * w0, b1 = wb * w1, b2 = wb * w2, b3 = wb * w3;   // WB*W11 ... formed first, as the reference's left-to-right product
+      wo_plain = wo_plain + wb;
+#pragma unroll
+      for (int f = 0; f < KF; f++) {
+        const int k = min(k0 + f, a.kc - 1);
+        const R* __restrict__ g = a.gi + (size_t)k * a.mi;
+        if (!((maskbits >> f) & 1u)) {
+          const R gb = w0 * __ldg(g + (i0 - 1)) + w1 * __ldg(g + (i1 - 1)) + w2 * __ldg(g + (i2 - 1)) + w3 * __ldg(g + (i3 - 1));
+          acc[f] = acc[f] + wb * gb;
+        } else {
+          // straight-line: every tap is loaded (the positions are valid), the bitmap only predicates the adds
+          const u8* __restrict__ l = a.li + (size_t)k * a.mi;
+          const u8 l0 = __ldg(l + (i0 - 1)), l1 = __ldg(l + (i1 - 1)), l2 = __ldg(l + (i2 - 1)), l3 = __ldg(l + (i3 - 1));
+          const R g0 = __ldg(g + (i0 - 1)), g1 = __ldg(g + (i1 - 1)), g2 = __ldg(g + (i2 - 1)), g3 = __ldg(g + (i3 - 1));
+          R ac = acc[f], wc = wo[f];
+          add2_if<R>(l0, ac, b0 * g0, wc, b0);
+          add2_if<R>(l1, ac, b1 * g1, wc, b1);
+          add2_if<R>(l2, ac, b2 * g2, wc, b2);
+          add2_if<R>(l3, ac, b3 * g3, wc, b3);
+          acc[f] = ac; wo[f] = wc;
+        }
+      }
+    }
+  }
+  if (!live) return;
+#pragma unroll
+  for (int f = 0; f < KF; f++) {
+    const int k = k0 + f;
+    if (k >= a.kc) break;
+    const R w = ((maskbits >> f) & 1u) ? wo[f] : wo_plain;
+    const bool good = w >= a.pmp;
+    const size_t oa = (size_t)k * a.mo + n;
+    __stcs(a.go + oa, good ? acc[f] / w : (R)0);
+    __stcs(a.lo + oa, (u8)(good ? 1 : 0));
     if (!good) a.flag[k] = 1;
   }
 }

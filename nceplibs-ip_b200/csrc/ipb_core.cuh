@@ -11,6 +11,7 @@
 #include "ipb_apply.cuh"
 #include "ipb_fast.cuh"
 #include "ipb_tiles.cuh"
+#include "ipb_budget.cuh"
 #include "ipb_state.h"
 
 namespace ipb {
@@ -56,13 +57,15 @@ void launch_apply(const Plan<R>& P, bool vec, FieldArgs<R> a, cudaStream_t st) {
     if (method == M_BILINEAR && !vec && tiles_ok(P, a)) { launch_bilinear_tiles(P, a, st); return; }
     if (method == M_BILINEAR && !vec && fast_bilinear_ok(P, a)) { launch_fast_bilinear(P, a, st); return; }
     const int kpb = std::max(1, std::min(a.kc, 64));   // fields per thread: the plan entry is re-read once per kpb fields
-    dim3 grid(nblk(no, 128), nblk(a.kc, kpb));
+    const int rowlen = patch_rowlen(P.gout.p, no);
+    dim3 grid = patch_grid(rowlen, no, 4);
+    grid.z = nblk(a.kc, kpb);
     if (method == M_BILINEAR) {
-      if (vec) k_apply_stencil<R, 2, true><<<grid, 128, 0, st>>>(a, gi, kpb, P.nxy, P.wxy, P.cxy, P.sxy, P.nc, P.x, P.y, P.crot, P.srot);
-      else k_apply_stencil<R, 2, false><<<grid, 128, 0, st>>>(a, gi, kpb, P.nxy, P.wxy, nullptr, nullptr, P.nc, P.x, P.y, nullptr, nullptr);
+      if (vec) k_apply_stencil<R, 2, true><<<grid, 128, 0, st>>>(a, gi, kpb, P.nxy, P.wxy, P.cxy, P.sxy, P.nc, P.x, P.y, P.crot, P.srot, rowlen);
+      else k_apply_stencil<R, 2, false><<<grid, 128, 0, st>>>(a, gi, kpb, P.nxy, P.wxy, nullptr, nullptr, P.nc, P.x, P.y, nullptr, nullptr, rowlen);
     } else {
-      if (vec) k_apply_stencil<R, 4, true><<<grid, 128, 0, st>>>(a, gi, kpb, P.nxy, P.wxy, P.cxy, P.sxy, P.nc, P.x, P.y, P.crot, P.srot);
-      else k_apply_stencil<R, 4, false><<<grid, 128, 0, st>>>(a, gi, kpb, P.nxy, P.wxy, nullptr, nullptr, P.nc, P.x, P.y, nullptr, nullptr);
+      if (vec) k_apply_stencil<R, 4, true><<<grid, 128, 0, st>>>(a, gi, kpb, P.nxy, P.wxy, P.cxy, P.sxy, P.nc, P.x, P.y, P.crot, P.srot, rowlen);
+      else k_apply_stencil<R, 4, false><<<grid, 128, 0, st>>>(a, gi, kpb, P.nxy, P.wxy, nullptr, nullptr, P.nc, P.x, P.y, nullptr, nullptr, rowlen);
     }
     g_launches++;
   } else if (method == M_NEIGHBOR) {
@@ -76,6 +79,12 @@ void launch_apply(const Plan<R>& P, bool vec, FieldArgs<R> a, cudaStream_t st) {
     constexpr int KF = 8;   // fields per thread: the sub-sample taps are re-read once per KF fields
     dim3 grid(nblk(no, 128), nblk(a.kc, KF));
     const int ns = P.bo.nsamp;
+    if (budget_collapsed_ok(P, a)) { launch_budget_collapsed(P, a, st); return; }
+    if (method == M_BUDGET && !vec && a.mspiral <= 1 && ns > 0) {
+      k_budget_scalar<R, KF><<<dim3(nblk(no, 32), nblk(a.kc, 8 * KF)), 256, 0, st>>>(a, ns, P.bn, P.bw, P.d_wb);
+      g_launches++;
+      return;
+    }
     if (method == M_BUDGET) {
       if (vec) k_apply_budget<R, false, true, KF><<<grid, 128, 0, st>>>(a, gi, ns, P.bn, P.bw, P.bc, P.bs, P.d_wb, P.rlat, P.rlon, P.crot, P.srot);
       else k_apply_budget<R, false, false, KF><<<grid, 128, 0, st>>>(a, gi, ns, P.bn, P.bw, nullptr, nullptr, P.d_wb, P.rlat, P.rlon, nullptr, nullptr);
@@ -156,6 +165,7 @@ void run(bool vec, int dev, void* user_stream, i64 ip, const i64* ipopt, const G
   if (!P) {
     P.reset(build_plan<R>(method, vec, ipopt, gin, gout, mi, mo, no, rlat, rlon, crot, srot, st0));
     if (P->iret == 0 && !station) { build_tile_tables<R>(*P, st0); P->bytes += P->tiles.bytes; }
+    if (P->iret == 0) build_budget_collapse<R>(*P, st0);
     if (!station) cache_put<R>(key, P);
   }
   cudaEventRecord(t1, st0);

@@ -86,6 +86,10 @@ template <class R> struct Plan {
   R* bw = nullptr;            // [nsamp][4][no] (budget only)
   R *bc = nullptr, *bs = nullptr;  // [nsamp][bt][no] (vector)
   R* d_wb = nullptr;          // [nsamp]
+  // collapsed budget taps of the binary64 kinds (ipb_budget.cuh): cu = taps per point in use (0 = not available)
+  int cu = 0;
+  int* cn = nullptr;          // [16][no] distinct source positions (padded with a valid position)
+  R *cw = nullptr, *cwsum = nullptr;  // [16][no] summed weights (padding 0); [no] sum of the sample weights
   // poles (lat-lon outputs): POLFIXS / POLFIXV
   int npn = 0, nps = 0;
   int *pole_n = nullptr, *pole_s = nullptr;  // 0-based output indices, ascending
@@ -99,7 +103,7 @@ template <class R> struct Plan {
 
   ~Plan() {
     dfree(d_tab_in); dfree(d_tab_out); dfree(rlat); dfree(rlon); dfree(crot); dfree(srot); dfree(x); dfree(y);
-    dfree(nxy); dfree(wxy); dfree(cxy); dfree(sxy); dfree(nc); dfree(bn); dfree(bw); dfree(bc); dfree(bs); dfree(d_wb);
+    dfree(nxy); dfree(wxy); dfree(cxy); dfree(sxy); dfree(nc); dfree(bn); dfree(bw); dfree(bc); dfree(bs); dfree(d_wb); dfree(cn); dfree(cw); dfree(cwsum);
     dfree(pole_n); dfree(pole_s); dfree(pclon_n); dfree(pslon_n); dfree(pclon_s); dfree(pslon_s);
     for (int v = 0; v < 4; v++) { dfree(tiles.cid[v]); dfree(tiles.ncell[v]); dfree(tiles.cells[v]); dfree(tiles.edst[v]); }
     dfree(wq); dfree(ws2);
