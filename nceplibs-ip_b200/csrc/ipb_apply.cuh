@@ -26,6 +26,11 @@ template <class R> struct FieldArgs {
   int mcon, mspiral;
 };
 
+// ibo bookkeeping: flag[k] != 0 means some lo(:,k) is false.  Hundreds of thousands of threads may want to
+// set the same word; writing only when the (L1-cached, possibly stale) value is still zero keeps that down to
+// about one store per SM and field instead of one per warp, which would serialise in a single L2 slice.
+__device__ __forceinline__ void mark_bad(int* flag, int k) { if (flag[k] == 0) flag[k] = 1; }
+
 // Spiral search around (x,y): e.g. bilinear_interp_mod.F90:224-253.  Returns the 1-based
 // position of the first acceptable point, 0 if none.  first = 1 (bilinear) or 2 (others).
 template <class R>
@@ -191,7 +196,7 @@ k_apply_stencil(FieldArgs<R> a, GridP<R> gin, int kpb, const int* __restrict__ n
     a.go[oa] = og;
     if (VEC) a.vo[oa] = ov;
     a.lo[oa] = good ? 1 : 0;
-    if (!good) a.flag[k] = 1;
+    if (!good) mark_bad(a.flag, k);
   }
 }
 
@@ -237,7 +242,7 @@ k_apply_neighbor(FieldArgs<R> a, GridP<R> gin, int kpb, const int* __restrict__ 
     a.go[oa] = og;
     if (VEC) a.vo[oa] = ov;
     a.lo[oa] = p > 0 ? 1 : 0;
-    if (p <= 0) a.flag[k] = 1;
+    if (p <= 0) mark_bad(a.flag, k);
   }
 }
 
@@ -355,7 +360,7 @@ k_apply_budget(FieldArgs<R> a, GridP<R> gin, int nsamp, const int* __restrict__ 
     a.go[oa] = og;
     if (VEC) a.vo[oa] = ov;
     a.lo[oa] = good ? 1 : 0;
-    if (!good) a.flag[k] = 1;
+    if (!good) mark_bad(a.flag, k);
   }
 }
 
@@ -448,7 +453,7 @@ k_budget_scalar(FieldArgs<R> a, int nsamp, const int* __restrict__ bn, const R* 
     const size_t oa = (size_t)k * a.mo + n;
     __stcs(a.go + oa, good ? acc[f] / w : (R)0);
     __stcs(a.lo + oa, (u8)(good ? 1 : 0));
-    if (!good) a.flag[k] = 1;
+    if (!good) mark_bad(a.flag, k);
   }
 }
 

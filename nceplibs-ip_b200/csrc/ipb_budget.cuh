@@ -105,6 +105,7 @@ k_budget_collapsed(FieldArgs<R> a, int kpb, int nsamp, const int* __restrict__ c
 #pragma unroll
   for (int u = 0; u < U; u++) { s_off[u][tid] = cn[(size_t)u * a.no + n] - 1; s_w[u][tid] = cw[(size_t)u * a.no + n]; }
   const R wplain = wsum[n];
+  const R rwplain = wplain > 0 ? (R)1 / wplain : (R)0;   // the collapsed path is held to 1e-12, not to the last bit: multiply instead of divide
   const int k0 = blockIdx.y * kpb, k1 = min(k0 + kpb, a.kc);
   const int no = a.no;
   const R pmp = a.pmp;
@@ -129,7 +130,12 @@ k_budget_collapsed(FieldArgs<R> a, int kpb, int nsamp, const int* __restrict__ c
     if (__all_sync(__activemask(), mb == (1u << U) - 1u)) {
 #pragma unroll
       for (int u = 0; u < U; u++) acc = acc + s_w[u][tid] * v[u];
-      wo = wplain;
+      const bool good = wplain >= pmp;
+      __stcs(go, good ? acc * rwplain : (R)0);
+      __stcs(lo, (u8)(good ? 1 : 0));
+      if (!good) mark_bad(a.flag, k);
+      g += a.mi; if (l) l += a.mi; go += a.mo; lo += a.mo;
+      continue;
     } else {
       wo = 0;
 #pragma unroll
@@ -143,7 +149,7 @@ k_budget_collapsed(FieldArgs<R> a, int kpb, int nsamp, const int* __restrict__ c
     const bool good = wo >= pmp;
     __stcs(go, good ? acc / wo : (R)0);
     __stcs(lo, (u8)(good ? 1 : 0));
-    if (!good) a.flag[k] = 1;
+    if (!good) mark_bad(a.flag, k);
     g += a.mi; if (l) l += a.mi; go += a.mo; lo += a.mo;
   }
 }

@@ -145,7 +145,7 @@ k_bilinear_stream(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restri
         for (int p = 0; p < 4; p++)
           if (n0 + p >= 0 && n0 + p < a.no) { a.go[ob + n0 + p] = o[p]; a.lo[ob + n0 + p] = (u8)((lw >> (8 * p)) & 1u); }
       }
-      if (bad) a.flag[k] = 1;
+      if (bad) mark_bad(a.flag, k);
     }
   }
 }
@@ -199,14 +199,14 @@ k_neighbor_lane(FieldArgs<R> a, const int* __restrict__ nxy, int kpb, int rowlen
       __stcs(go, ok ? __ldg(g) : (R)0); __stcs(lo, ok);
       g += a.mi; go += a.mo; lo += a.mo;
     }
-    if (!ok) for (int kk = k0; kk < k1; kk++) a.flag[kk] = 1;
+    if (!ok) for (int kk = k0; kk < k1; kk++) mark_bad(a.flag, kk);
     return;
   }
   const u8* __restrict__ l = a.li + (size_t)k0 * a.mi + (p0 > 0 ? p0 - 1 : 0);
   for (int k = k0; k < k1; k++) {
     const bool ok = p0 > 0 && (a.ibi[k] == 0 || *l);
     __stcs(go, ok ? __ldg(g) : (R)0); __stcs(lo, (u8)(ok ? 1 : 0));
-    if (!ok) a.flag[k] = 1;
+    if (!ok) mark_bad(a.flag, k);
     g += a.mi; l += a.mi; go += a.mo; lo += a.mo;
   }
 }

@@ -410,7 +410,7 @@ k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restric
           for (int p = 0; p < 4; p++)
             if (n0 + p >= 0 && n0 + p < a.no) { gop[p] = o[p]; lop[p] = (u8)((lw >> (8 * p)) & 1u); }
         }
-        if (bad) a.flag[k] = 1;
+        if (bad) mark_bad(a.flag, k);
         gop += ostep; lop += ostep;
       }
     }
