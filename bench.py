@@ -112,7 +112,7 @@ class ClockSampler:
                     self.rows.append([x.strip() for x in o.split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.05)
 
     def __enter__(self):
         self.t = threading.Thread(target=self._run, daemon=True)
@@ -525,7 +525,7 @@ def run_e2e(args, wl, lib, L, torch, dist, dev, world, gin, gout, mi, mo, km, no
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="bilinear", choices=sorted(WORKLOADS))
