@@ -220,6 +220,58 @@ template <class R> __device__ __forceinline__ R quot_near1(R g, R w, R rw) {
   r = fma_r<R>(-q1, w, g);
   return fma_r<R>(r, rw, q1);
 }
+// ---- packed binary32 arithmetic (sm_100 FMUL2 / FFMA2: two IEEE operations per issued instruction) ----------
+// Used where the reference's operation is exactly a pair of independent multiplies or a pair of independent
+// fused steps of the quotient.  Multiplies are never followed by a packed add (ptxas 12.9 fuses a packed
+// mul.rn + add.rn pair into FFMA2 even with --fmad false, which would change the rounding): the adds of the
+// tap sum stay scalar.
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&r)) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return r;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(*reinterpret_cast<unsigned long long*>(&r)) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)), "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return r;
+}
+// the four tap sums and quotients of one thread and field: generic form
+template <class R> struct Quad {
+  static __device__ __forceinline__ void run(const CellRec<R> (&rec)[4], const R (&w)[4][4], const R (&W)[4], const R (&rW)[4], R (&G)[4], R (&o)[4]) {
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+      // the reference starts from G=0; 0 + x only changes x = -0, which the quotient maps to +0 again
+      R g = w[p][0] * rec[p].get(0);
+#pragma unroll
+      for (int t = 1; t < 4; t++) g = g + w[p][t] * rec[p].get(t);
+      G[p] = g;
+      o[p] = quot_near1<R>(g, W[p], rW[p]);
+    }
+  }
+};
+// binary32: the same operations with the products and the quotient steps issued two at a time
+template <> struct Quad<float> {
+  static __device__ __forceinline__ void run(const CellRec<float> (&rec)[4], const float (&w)[4][4], const float (&W)[4], const float (&rW)[4],
+                                             float (&G)[4], float (&o)[4]) {
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+      const float2 pa = mul2(make_float2(w[p][0], w[p][1]), make_float2(rec[p].v.x, rec[p].v.y));
+      const float2 pb = mul2(make_float2(w[p][2], w[p][3]), make_float2(rec[p].v.z, rec[p].v.w));
+      G[p] = ((pa.x + pa.y) + pb.x) + pb.y;
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const float2 g = make_float2(G[2 * h], G[2 * h + 1]);
+      const float2 nw = make_float2(-W[2 * h], -W[2 * h + 1]), rw = make_float2(rW[2 * h], rW[2 * h + 1]);
+      float2 r = fma2(g, nw, g);
+      const float2 q1 = fma2(r, rw, g);
+      r = fma2(q1, nw, g);
+      const float2 q = fma2(r, rw, q1);
+      o[2 * h] = q.x; o[2 * h + 1] = q.y;
+    }
+  }
+};
+
 template <class R> __device__ __forceinline__ R win_lo() { return sizeof(R) == 4 ? (R)6.5e-27f : (R)1e-187; }   // ~2^-87 / 2^-620
 template <class R> __device__ __forceinline__ R win_hi() { return sizeof(R) == 4 ? (R)1.5e26f : (R)1e187; }
 template <class R> __device__ __forceinline__ R abs_r(R x);
@@ -356,16 +408,7 @@ k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restric
         rec[2] = same2a ? rec[0] : rec[3];
         if (own1) rec[1] = *reinterpret_cast<const CellRec<R>*>(&sb[f * CMAX * 4 + coff[1]]);
         if (own2) rec[2] = *reinterpret_cast<const CellRec<R>*>(&sb[f * CMAX * 4 + coff[2]]);
-#pragma unroll
-        for (int p = 0; p < 4; p++) {
-          const CellRec<R>& c = rec[p];
-          // the reference starts from G=0; 0 + x only changes x = -0, which the quotient maps to +0 again
-          R g = w[p][0] * c.get(0);
-#pragma unroll
-          for (int t = 1; t < 4; t++) g = g + w[p][t] * c.get(t);
-          G[p] = g;
-          o[p] = quot_near1<R>(g, W[p], rW[p]);
-        }
+        Quad<R>::run(rec, w, W, rW, G, o);
         const R amax = max_r<R>(max_r<R>(abs_r<R>(G[0]), abs_r<R>(G[1])), max_r<R>(abs_r<R>(G[2]), abs_r<R>(G[3])));
         const R amin = min_r<R>(min_r<R>(abs_r<R>(G[0]), abs_r<R>(G[1])), min_r<R>(abs_r<R>(G[2]), abs_r<R>(G[3])));
         if (!(amax < win_hi<R>() && amin >= win_lo<R>())) {
