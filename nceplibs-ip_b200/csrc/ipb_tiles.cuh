@@ -284,6 +284,9 @@ template <class R> __device__ __forceinline__ R min_r(R a, R b);
 template <> __device__ __forceinline__ float min_r<float>(float a, float b) { return fminf(a, b); }
 template <> __device__ __forceinline__ double min_r<double>(double a, double b) { return fmin(a, b); }
 
+#ifndef IPB_TILES_NBUF
+#define IPB_TILES_NBUF 2
+#endif
 #ifndef IPB_TILES_MINBLOCKS
 #define IPB_TILES_MINBLOCKS (sizeof(R) == 4 ? 4 : 3)
 #endif
@@ -298,7 +301,8 @@ k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restric
   constexpr int BUF = F * CMAX * 4;                 // elements per buffer
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  R* sm = reinterpret_cast<R*>(sm_raw) + warp * 2 * BUF;
+  constexpr int NBUF = IPB_TILES_NBUF;               // staging depth: passes in flight ahead of the one being computed + 1
+  R* sm = reinterpret_cast<R*>(sm_raw) + warp * NBUF * BUF;
   const int cls = blockIdx.x & 3, slice = blockIdx.x >> 2, tile = blockIdx.y * TILE_WARPS + warp;
   if (tile >= T.ntile) return;
   const int variant = (base_mis + cls * (a.mo & 3)) & 3;
@@ -377,14 +381,18 @@ k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restric
   R* gop = a.go + ((size_t)(cls + 4 * jbeg) * a.mo + n0);   // this thread's 4 points in the next field to write
   u8* lop = a.lo + ((size_t)(cls + 4 * jbeg) * a.mo + n0);
   const size_t ostep = 4 * (size_t)a.mo;
-  int buf = 0;
-  for (int j0 = jbeg; j0 < jend; j0 += F, buf ^= 1) {
-    if (j0 + F < jend) {
-      stage(buf ^ 1, j0 + F);
-      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    }
+  // prologue: NBUF-1 passes in flight (an empty group is committed where there is no pass, so that the
+  // group count below is uniform)
+#pragma unroll
+  for (int b = 1; b < NBUF - 1; b++) {
+    if (jbeg + b * F < jend) stage(b, jbeg + b * F);
+    else asm volatile("cp.async.commit_group;\n" ::: "memory");
+  }
+  int buf = 0, nxt = NBUF - 1;
+  for (int j0 = jbeg; j0 < jend; j0 += F) {
+    if (j0 + (NBUF - 1) * F < jend) stage(nxt, j0 + (NBUF - 1) * F);
+    else asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(NBUF - 1) : "memory");
     __syncwarp();
     const R* __restrict__ sb = sm + buf * BUF;
     if (j0 - jm0 >= 32) {
@@ -458,6 +466,8 @@ k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restric
       }
     }
     __syncwarp();
+    buf = buf + 1 == NBUF ? 0 : buf + 1;
+    nxt = nxt + 1 == NBUF ? 0 : nxt + 1;
   }
 }
 
@@ -479,7 +489,7 @@ template <class R> void launch_bilinear_tiles(const Plan<R>& P, const FieldArgs<
   const int ni = (4 * T.max_cells + 31) / 32;       // staging copies per lane and field
 #define IPB_TILES_LAUNCH(FF, NN)                                                                                          \
   {                                                                                                                       \
-    constexpr int SM = TILE_WARPS * 2 * (FF) * (8 * (NN)) * 4 * (int)sizeof(R);                                           \
+    constexpr int SM = TILE_WARPS * IPB_TILES_NBUF * (FF) * (8 * (NN)) * 4 * (int)sizeof(R);                                           \
     static bool once = false;                                                                                             \
     if (!once) { IPB_CUDA(cudaFuncSetAttribute(k_bilinear_tiles<R, FF, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); once = true; } \
     k_bilinear_tiles<R, FF, NN><<<grid, TILE_THREADS, SM, st>>>(a, P.nxy, P.wq, P.ws2, D, base_mis, kpt);                       \
