@@ -530,12 +530,20 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="bilinear", choices=sorted(WORKLOADS))
     ap.add_argument("--km", type=int, default=0, help="fields per GPU (default: the workload's)")
+    ap.add_argument("--kind", default="", choices=["", "4", "d", "8"], help="build kind override (default: the workload's)")
+    ap.add_argument("--mask", type=int, default=-1, help="1: every field carries the land-mask bitmap, 0: none (default: the workload's)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 1)
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.kind:
+        wl["kind"] = args.kind
+        wl["desc"] += f" [kind override _{args.kind}]"
+    if args.mask >= 0:
+        wl["mask"] = bool(args.mask)
+        wl["desc"] += f" [bitmap override {args.mask}]"
     if args.impl == "reference":
         run_reference(args, wl)
     else:

@@ -294,7 +294,10 @@ template <> __device__ __forceinline__ double min_r<double>(double a, double b) 
 // Each warp is an independent tile: it stages its own cells into its own shared-memory slice
 // (double buffered: the copies of pass s+1 are in flight while pass s is computed) and never
 // meets a block-wide barrier.
-template <class R, int F, int NI>
+// MASKED = the batch contains fields with a bitmap: their li bytes are staged next to the values (one packed
+// word per cell) and those fields are computed from shared memory too, tap by tap with the IEEE division,
+// instead of falling back to global gathers.
+template <class R, int F, int NI, bool MASKED>
 __global__ void __launch_bounds__(TILE_THREADS, IPB_TILES_MINBLOCKS)
 k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restrict__ wq, const R* __restrict__ ws2, TileDev T, int base_mis, int kpt) {
   constexpr int CMAX = 8 * NI;                      // cells a tile may have
@@ -303,6 +306,7 @@ k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restric
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NBUF = IPB_TILES_NBUF;               // staging depth: passes in flight ahead of the one being computed + 1
   R* sm = reinterpret_cast<R*>(sm_raw) + warp * NBUF * BUF;
+  u8* smask = sm_raw + (size_t)TILE_WARPS * NBUF * BUF * sizeof(R) + (size_t)warp * F * CMAX * 4;   // [F][cell*4 + tap] (MASKED only)
   const int cls = blockIdx.x & 3, slice = blockIdx.x >> 2, tile = blockIdx.y * TILE_WARPS + warp;
   if (tile >= T.ntile) return;
   const int variant = (base_mis + cls * (a.mo & 3)) & 3;
@@ -317,11 +321,13 @@ k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restric
   const R* gp[NI];                                  // source address of entry i in the next field to stage
   unsigned sdst[NI];                                // its shared-memory address in buffer 0, field 0
   bool act[NI];
+  int srci[MASKED ? NI : 1], slot[MASKED ? NI : 1];   // MASKED: source position and shared-memory slot of each entry, for the bitmap bytes
 #pragma unroll
   for (int i = 0; i < NI; i++) {
     const int q = lane + 32 * i;
     const int src = q < T.cstride ? esrc[q] : -1;
     act[i] = src >= 0;
+    if (MASKED) { srci[i] = act[i] ? src : 0; slot[i] = act[i] ? (int)edst[q] : 0; }
     gp[i] = a.gi + (size_t)(cls + 4 * jbeg) * a.mi + (act[i] ? src : 0);
     sdst[i] = (unsigned)__cvta_generic_to_shared(sm + (act[i] ? (int)edst[q] : 0));
   }
@@ -354,7 +360,7 @@ k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restric
   // ---- per-thread plan data: weights, weight sums, cell numbers ----
   R w[4][4], W[4], rW[4];
   int coff[4];
-  bool full = true;
+  bool full = true, incell = true;   // full: the fast quotient path applies; incell: all four points have a staged cell
   const unsigned packed = reinterpret_cast<const unsigned*>(T.cid[variant])[(size_t)tile * 32 + lane];
 #pragma unroll
   for (int p = 0; p < 4; p++) {
@@ -375,6 +381,7 @@ k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restric
     coff[p] = c * 4;
     const R dev = ws - (R)1;
     full = full && in && c != 0xff && ws >= a.pmp && dev <= (R)9.5e-7 && dev >= (R)-9.5e-7;
+    incell = incell && in && c != 0xff;
   }
   const bool same1a = coff[1] == coff[0], same2a = coff[2] == coff[0];
   const bool own1 = !same1a && coff[1] != coff[3], own2 = !same2a && coff[2] != coff[3];
@@ -401,6 +408,18 @@ k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restric
     }
     // ---- compute ----
     const bool plain = full && (j0 + F <= jend) && ((maskbits >> (j0 - jm0)) & ((1u << F) - 1u)) == 0;
+    const unsigned passmask = MASKED ? ((maskbits >> (j0 - jm0)) & ((1u << F) - 1u)) : 0u;   // bit f: field f of the pass has a bitmap
+    if (MASKED && passmask) {
+      // the bitmap bytes of this pass's masked fields, at the positions of the staging list
+      for (int f = 0; f < F && j0 + f < jend; f++) {
+        if (!((passmask >> f) & 1u)) continue;
+        const u8* __restrict__ l = a.li + (size_t)(cls + 4 * (j0 + f)) * a.mi;
+#pragma unroll
+        for (int i = 0; i < NI; i++)
+          if (act[i]) smask[f * CMAX * 4 + slot[i]] = __ldg(l + srci[i]);
+      }
+      __syncwarp();
+    }
     if (plain) {
 #pragma unroll
       for (int f = 0; f < F; f++) {
@@ -442,6 +461,26 @@ k_bilinear_tiles(FieldArgs<R> a, const int* __restrict__ nxy, const R* __restric
         R o[4];
         unsigned lw = 0;
         bool bad = false;
+        if (MASKED && incell) {
+          // from the staged records: the reference's loop body, taps in its order, IEEE division
+#pragma unroll
+          for (int p = 0; p < 4; p++) {
+            const CellRec<R> c = *reinterpret_cast<const CellRec<R>*>(&sb[f * CMAX * 4 + coff[p]]);
+            const unsigned mw = masked ? *reinterpret_cast<const unsigned*>(&smask[f * CMAX * 4 + coff[p]]) : 0x01010101u;
+            R Gp = 0, Wp = 0;
+#pragma unroll
+            for (int t = 0; t < 4; t++)
+              if ((mw >> (8 * t)) & 0xffu) { Gp = Gp + w[p][t] * c.get(t); Wp = Wp + w[p][t]; }
+            const bool good = Wp >= a.pmp;
+            o[p] = good ? Gp / Wp : (R)0;
+            if (good) lw |= 1u << (8 * p); else bad = true;
+          }
+          store4<R>(gop, o[0], o[1], o[2], o[3]);
+          __stcs(reinterpret_cast<unsigned*>(lop), lw);
+          if (bad) mark_bad(a.flag, k);
+          gop += ostep; lop += ostep;
+          continue;
+        }
 #pragma unroll
         for (int p = 0; p < 4; p++) {
           const int n = n0 + p;
@@ -487,19 +526,21 @@ template <class R> void launch_bilinear_tiles(const Plan<R>& P, const FieldArgs<
   const int kpt = std::max(32, std::min(kpt_env, ((per_class + 31) / 32) * 32));   // fields of one class per warp (multiple of 32)
   dim3 grid(4 * nblk(per_class, kpt), nblk(T.ntile, TILE_WARPS));
   const int ni = (4 * T.max_cells + 31) / 32;       // staging copies per lane and field
-#define IPB_TILES_LAUNCH(FF, NN)                                                                                          \
+#define IPB_TILES_LAUNCH_M(FF, NN, MM)                                                                                    \
   {                                                                                                                       \
-    constexpr int SM = TILE_WARPS * IPB_TILES_NBUF * (FF) * (8 * (NN)) * 4 * (int)sizeof(R);                                           \
+    constexpr int SM = TILE_WARPS * (IPB_TILES_NBUF * (FF) * (8 * (NN)) * 4 * (int)sizeof(R) + ((MM) ? (FF) * (8 * (NN)) * 4 : 0)); \
     static bool once = false;                                                                                             \
-    if (!once) { IPB_CUDA(cudaFuncSetAttribute(k_bilinear_tiles<R, FF, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); once = true; } \
-    k_bilinear_tiles<R, FF, NN><<<grid, TILE_THREADS, SM, st>>>(a, P.nxy, P.wq, P.ws2, D, base_mis, kpt);                       \
+    if (!once) { IPB_CUDA(cudaFuncSetAttribute(k_bilinear_tiles<R, FF, NN, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); once = true; } \
+    k_bilinear_tiles<R, FF, NN, MM><<<grid, TILE_THREADS, SM, st>>>(a, P.nxy, P.wq, P.ws2, D, base_mis, kpt);              \
   }
+#define IPB_TILES_LAUNCH(FF, NN) { if (a.li) IPB_TILES_LAUNCH_M(FF, NN, true) else IPB_TILES_LAUNCH_M(FF, NN, false) }
   if (ni <= 2) IPB_TILES_LAUNCH(F, 2)
   else if (ni <= 3) IPB_TILES_LAUNCH(F, 3)
   else if (ni <= 4) IPB_TILES_LAUNCH(F, 4)
   else if (ni <= 6) IPB_TILES_LAUNCH(F8, 6)
   else IPB_TILES_LAUNCH(F8, 8)
 #undef IPB_TILES_LAUNCH
+#undef IPB_TILES_LAUNCH_M
   g_launches++;
 }
 
