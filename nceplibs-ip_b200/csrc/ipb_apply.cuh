@@ -105,41 +105,61 @@ k_apply_stencil(FieldArgs<R> a, GridP<R> gin, int kpb, const int* __restrict__ n
     const u8* __restrict__ l = a.li ? a.li + (size_t)k * a.mi : nullptr;
     const size_t oa = (size_t)k * a.mo + n;
     if (complete && !masked) {   // complete also means the weight sum passes the threshold
-      R G = 0, V = 0;
-      R gmin = DM<R>::huge(), gmax = -DM<R>::huge(), vmin = DM<R>::huge(), vmax = -DM<R>::huge();
-      R tv[T2], tu[VEC ? T2 : 1];
+      // KU fields per iteration with all their gathers issued first: this loop is bound by gather latency
+      constexpr int KU = (NT == 2) ? 2 : 1;
+      const int ku = (KU == 2 && k + 1 < k1 && a.ibi[k + 1] == 0) ? 2 : 1;
+      R tv[KU][T2], tu[KU][VEC ? T2 : 1];
 #pragma unroll
-      for (int t = 0; t < T2; t++) { tv[t] = __ldg(g + (idx[t] - 1)); if (VEC) tu[t] = __ldg(gv + (idx[t] - 1)); }
+      for (int q = 0; q < KU; q++) {
+        if (q < ku) {
+          const R* __restrict__ gq = g + (size_t)q * a.mi;
+          const R* __restrict__ gvq = VEC ? gv + (size_t)q * a.mi : nullptr;
 #pragma unroll
-      for (int t = 0; t < T2; t++) {
-        if (!VEC) {
-          G = G + w[t] * tv[t];
-          if (NT == 4 && a.mcon > 0) { gmin = DM<R>::vmin(gmin, tv[t]); gmax = DM<R>::vmax(gmax, tv[t]); }
-        } else {
-          const R u = tv[t], v = tu[t];
-          const R ur = c[t] * u - s[t] * v;
-          const R vr = s[t] * u + c[t] * v;
-          G = G + w[t] * ur;
-          V = V + w[t] * vr;
-          if (NT == 4 && a.mcon > 0) {
-            gmin = DM<R>::vmin(gmin, ur); gmax = DM<R>::vmax(gmax, ur);
-            vmin = DM<R>::vmin(vmin, vr); vmax = DM<R>::vmax(vmax, vr);
-          }
+          for (int t = 0; t < T2; t++) { tv[q][t] = __ldg(gq + (idx[t] - 1)); if (VEC) tu[q][t] = __ldg(gvq + (idx[t] - 1)); }
         }
       }
-      R og, ov = 0;
-      if (!VEC) {
-        og = G / Wall;
-        if (NT == 4 && a.mcon > 0) og = DM<R>::vmin(DM<R>::vmax(og, gmin), gmax);
-      } else {
-        const R ur = cr * G - sr * V;
-        const R vr = sr * G + cr * V;
-        og = ur / Wall; ov = vr / Wall;
-        if (NT == 4 && a.mcon > 0) { og = DM<R>::vmin(DM<R>::vmax(og, gmin), gmax); ov = DM<R>::vmin(DM<R>::vmax(ov, vmin), vmax); }
+#pragma unroll
+      for (int q = 0; q < KU; q++) {
+        if (q >= ku) break;
+        R G = 0, V = 0;
+        R gmin = DM<R>::huge(), gmax = -DM<R>::huge(), vmin = DM<R>::huge(), vmax = -DM<R>::huge();
+        const bool clampit = NT == 4 && a.mcon > 0;
+#pragma unroll
+        for (int t = 0; t < T2; t++) {
+          if (!VEC) {
+            G = G + w[t] * tv[q][t];
+          } else {
+            const R u = tv[q][t], v = tu[q][t];
+            const R ur = c[t] * u - s[t] * v;
+            const R vr = s[t] * u + c[t] * v;
+            G = G + w[t] * ur;
+            V = V + w[t] * vr;
+            if (clampit) {
+              gmin = DM<R>::vmin(gmin, ur); gmax = DM<R>::vmax(gmax, ur);
+              vmin = DM<R>::vmin(vmin, vr); vmax = DM<R>::vmax(vmax, vr);
+            }
+          }
+        }
+        if (!VEC && clampit) {   // separate pass: the common unconstrained case pays nothing for it
+#pragma unroll
+          for (int t = 0; t < T2; t++) { gmin = DM<R>::vmin(gmin, tv[q][t]); gmax = DM<R>::vmax(gmax, tv[q][t]); }
+        }
+        R og, ov = 0;
+        if (!VEC) {
+          og = G / Wall;
+          if (clampit) og = DM<R>::vmin(DM<R>::vmax(og, gmin), gmax);
+        } else {
+          const R ur = cr * G - sr * V;
+          const R vr = sr * G + cr * V;
+          og = ur / Wall; ov = vr / Wall;
+          if (clampit) { og = DM<R>::vmin(DM<R>::vmax(og, gmin), gmax); ov = DM<R>::vmin(DM<R>::vmax(ov, vmin), vmax); }
+        }
+        const size_t ob = oa + (size_t)q * a.mo;
+        __stcs(a.go + ob, og);
+        if (VEC) __stcs(a.vo + ob, ov);
+        __stcs(a.lo + ob, (u8)1);
       }
-      __stcs(a.go + oa, og);
-      if (VEC) __stcs(a.vo + oa, ov);
-      __stcs(a.lo + oa, (u8)1);
+      k += ku - 1;
       continue;
     }
     R G = 0, V = 0, W = 0;
