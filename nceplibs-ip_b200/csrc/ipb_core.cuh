@@ -12,6 +12,7 @@
 #include "ipb_fast.cuh"
 #include "ipb_tiles.cuh"
 #include "ipb_budget.cuh"
+#include "ipb_gtiles.cuh"
 #include "ipb_state.h"
 
 namespace ipb {
@@ -53,6 +54,7 @@ void launch_apply(const Plan<R>& P, bool vec, FieldArgs<R> a, cudaStream_t st) {
   if (no <= 0 || a.kc <= 0) return;
   const GridP<R>& gi = P.gin.p;
   const int method = P.method;
+  if (gtiles_ok(P, a)) { launch_gtiles(P, a, st); return; }
   if (method == M_BILINEAR || method == M_BICUBIC) {
     if (method == M_BILINEAR && !vec && tiles_ok(P, a)) { launch_bilinear_tiles(P, a, st); return; }
     if (method == M_BILINEAR && !vec && fast_bilinear_ok(P, a)) { launch_fast_bilinear(P, a, st); return; }
@@ -166,6 +168,7 @@ void run(bool vec, int dev, void* user_stream, i64 ip, const i64* ipopt, const G
     P.reset(build_plan<R>(method, vec, ipopt, gin, gout, mi, mo, no, rlat, rlon, crot, srot, st0));
     if (P->iret == 0 && !station) { build_tile_tables<R>(*P, st0); P->bytes += P->tiles.bytes; }
     if (P->iret == 0) build_budget_collapse<R>(*P, st0);
+    if (P->iret == 0 && !station) { build_gtiles<R>(*P, st0); P->bytes += P->gt.bytes; }
     if (!station) cache_put<R>(key, P);
   }
   cudaEventRecord(t1, st0);

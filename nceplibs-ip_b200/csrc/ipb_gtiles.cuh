@@ -1,0 +1,622 @@
+// ipb200 — point-staged apply kernels for the methods whose stencils are not 2x2 cells: bicubic
+// (bicubic_interp_mod.F90:226-272), neighbor (neighbor_interp_mod.F90:213-263) and the collapsed budget
+// taps of the binary64 kinds (budget_interp_mod.F90:252-344 through ipb_budget.cuh).
+//
+// The general kernels gather every tap of every output point from global memory for every field: 16
+// (bicubic), 9 (+9 bitmap bytes, budget) or 1 (neighbor) scattered loads per point and field, each a
+// handful of 32-byte sectors per warp instruction.  That is what bounds them (L1 tag-stage wavefronts), not
+// HBM.  Here the gathers leave the field loop:
+//
+//  * the output points are cut into TILES of 128 points — 128 consecutive points, or a 32x4 / 16x8 patch of
+//    the output grid, whichever needs the fewest distinct source points (decided per plan by counting);
+//  * at plan time every tile gets the sorted list of the DISTINCT source positions its points refer to
+//    (at most 256), and every tap of every point the one-byte number ("slot") of its position in that list;
+//  * per pass of 8 fields the block copies those positions from each field into shared memory with
+//    cp.async — address-sorted, so one warp instruction touches few sectors — double buffered, and, for
+//    fields with a bitmap, the li bytes at the same positions packed as one bit per field;
+//  * the field loop of a thread (one output point) is then U shared-memory loads at precomputed offsets,
+//    the reference's multiply/adds in its order, the division and the go/lo stores — coalesced, 32
+//    consecutive points (or two runs of 16) per warp instruction.
+//
+// Arithmetic is the general kernels' (same operations, same order), so results are bit-identical to them.
+// Incomplete stencils, bitmap fields of the bicubic method and near-threshold budget sums take the same
+// general per-point code those kernels use.
+#pragma once
+#include <climits>
+#include <cstdlib>
+
+#include "ipb_budget.cuh"
+#include "ipb_tiles.cuh"
+
+namespace ipb {
+
+constexpr int GT_PTS = 128;       // output points per tile = threads per block
+constexpr int GT_MAXENT = 256;    // distinct source positions a tile may have (one-byte slots)
+constexpr int GT_F = 8;           // fields per staging pass
+
+__host__ __device__ inline int gt_point(const GtGeom& g, int tile, int r, int lane, int no) {
+  if (g.mode == 0) {
+    const long long n = (long long)tile * GT_PTS + 32 * r + lane;
+    return n < no ? (int)n : -1;
+  }
+  const int tx = tile % g.ntx, ty = tile / g.ntx;
+  int col, row;
+  if (g.mode == 1) { col = 32 * tx + lane; row = 4 * ty + r; }
+  else { col = 16 * tx + (lane & 15); row = 8 * ty + 2 * r + (lane >> 4); }
+  const long long n = (long long)row * g.rowlen + col;
+  return (col < g.rowlen && n < no) ? (int)n : -1;
+}
+inline GtGeom gt_geom(int mode, int rowlen, int no) {
+  GtGeom g;
+  g.mode = mode; g.rowlen = rowlen; g.ntx = 1;
+  if (mode == 0) { g.ntile = nblk(no, GT_PTS); return g; }
+  const int nrows = nblk(no, rowlen);
+  g.ntx = nblk(rowlen, mode == 1 ? 32 : 16);
+  g.ntile = g.ntx * nblk(nrows, mode == 1 ? 4 : 8);
+  return g;
+}
+
+// ---- plan time: the distinct source positions of every tile ----------------------------------------------
+// One block per tile.  write = 0: only count (maximum and total over tiles, to choose the tile shape);
+// write = 1: emit the sorted list esrc[tile][estride] (0-based, -1 = padding) and the slot of every tap.
+template <int NK>   // power of two >= 128 * U
+__global__ void __launch_bounds__(GT_PTS)
+k_gt_build(GtGeom g, int no, int U, const int* __restrict__ taps, int write, int estride, int* __restrict__ esrc,
+           u8* __restrict__ slot, int* gmax, unsigned long long* gsum, int* govf) {
+  __shared__ int key[NK];
+  __shared__ int part[GT_PTS + 1];
+  __shared__ int uniq[GT_MAXENT];
+  const int tid = threadIdx.x, tile = blockIdx.x;
+  const int n = gt_point(g, tile, tid >> 5, tid & 31, no);
+  for (int u = 0; u < U; u++) {
+    const int p = n >= 0 ? taps[(size_t)u * no + n] : 0;
+    key[u * GT_PTS + tid] = p > 0 ? p - 1 : INT_MAX;
+  }
+  for (int i = U * GT_PTS + tid; i < NK; i += GT_PTS) key[i] = INT_MAX;
+  __syncthreads();
+  for (int k = 2; k <= NK; k <<= 1) {          // bitonic sort, ascending
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < NK; i += GT_PTS) {
+        const int o = i ^ j;
+        if (o > i) {
+          const int x = key[i], y = key[o];
+          if ((x > y) == ((i & k) == 0)) { key[i] = y; key[o] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  constexpr int PER = NK / GT_PTS;
+  int cnt = 0;
+#pragma unroll
+  for (int q = 0; q < PER; q++) {
+    const int i = tid * PER + q, v = key[i];
+    if (v != INT_MAX && (i == 0 || key[i - 1] != v)) cnt++;
+  }
+  part[tid] = cnt;
+  __syncthreads();
+  if (tid == 0) {
+    int s = 0;
+    for (int t = 0; t < GT_PTS; t++) { const int c = part[t]; part[t] = s; s += c; }
+    part[GT_PTS] = s;
+  }
+  __syncthreads();
+  const int total = part[GT_PTS];
+  if (!write) {
+    if (tid == 0) { atomicMax(gmax, total); atomicAdd(gsum, (unsigned long long)total); if (total > GT_MAXENT) atomicAdd(govf, 1); }
+    return;
+  }
+  int pos = part[tid];
+#pragma unroll
+  for (int q = 0; q < PER; q++) {
+    const int i = tid * PER + q, v = key[i];
+    if (v != INT_MAX && (i == 0 || key[i - 1] != v)) { if (pos < GT_MAXENT) uniq[pos] = v; pos++; }
+  }
+  __syncthreads();
+  // a tile with more positions than the table holds is marked (-2): its points gather from global memory
+  const bool ovf = total > GT_MAXENT;
+  const int ne = ovf ? 0 : total;
+  for (int i = tid; i < estride; i += GT_PTS) esrc[(size_t)tile * estride + i] = i < ne ? uniq[i] : (ovf && i == 0 ? -2 : -1);
+  if (n < 0) return;
+  for (int u = 0; u < U; u++) {
+    const int p = taps[(size_t)u * no + n];
+    int s = 0;
+    if (p > 0 && ne > 0) {
+      int lo = 0, hi = ne - 1;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (uniq[mid] < p - 1) lo = mid + 1; else hi = mid; }
+      s = lo;
+    }
+    slot[(size_t)u * no + n] = (u8)s;
+  }
+}
+
+template <class R> void build_gtiles(Plan<R>& P, cudaStream_t st) {
+  GtTables& T = P.gt;
+  T = GtTables();
+  static const bool off = getenv("IPB_NO_GTILES") && atoi(getenv("IPB_NO_GTILES")) != 0;
+  if (off || P.vec || P.no <= 0) return;
+  const int* taps = nullptr;
+  int U = 0;
+  if (P.method == M_BICUBIC && P.nxy) { taps = P.nxy; U = 16; }
+  else if (P.method == M_NEIGHBOR && P.nxy) { taps = P.nxy; U = 1; }
+  else if (P.method == M_BUDGET && P.cu > 0 && P.cn) { taps = P.cn; U = P.cu; }
+  else return;
+  const int no = P.no;
+  const GridP<R>& go = P.gout.p;
+  int rowlen = 0;
+  if (go.type != P_STATION && go.im > 0 && go.jm > 0) rowlen = go.nscan == 0 ? go.im : go.jm;
+  const int nmode = (rowlen >= 16 && rowlen < no) ? 3 : 1;
+  int* d_max = dalloc<int>(8);
+  int* d_ovf = d_max + 4;
+  unsigned long long* d_sum = dalloc<unsigned long long>(4);
+  IPB_CUDA(cudaMemsetAsync(d_max, 0, 8 * sizeof(int), st));
+  IPB_CUDA(cudaMemsetAsync(d_sum, 0, 4 * sizeof(unsigned long long), st));
+  auto launch = [&](const GtGeom& g, int write, int estride, int m) {
+    if (U == 1) k_gt_build<128><<<g.ntile, GT_PTS, 0, st>>>(g, no, U, taps, write, estride, T.esrc, T.slot, d_max + m, d_sum + m, d_ovf + m);
+    else if (U <= 4) k_gt_build<512><<<g.ntile, GT_PTS, 0, st>>>(g, no, U, taps, write, estride, T.esrc, T.slot, d_max + m, d_sum + m, d_ovf + m);
+    else k_gt_build<2048><<<g.ntile, GT_PTS, 0, st>>>(g, no, U, taps, write, estride, T.esrc, T.slot, d_max + m, d_sum + m, d_ovf + m);
+    g_launches++;
+  };
+  for (int m = 0; m < nmode; m++) launch(gt_geom(m, rowlen, no), 0, 0, m);
+  int hmax[8];
+  int* hovf = hmax + 4;
+  unsigned long long hsum[4];
+  IPB_CUDA(cudaMemcpyAsync(hmax, d_max, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  IPB_CUDA(cudaMemcpyAsync(hsum, d_sum, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  IPB_CUDA(cudaStreamSynchronize(st));
+  if (getenv("IPB_DEBUG"))
+    for (int m = 0; m < nmode; m++)
+      fprintf(stderr, "ipb200: gtiles method %d U %d mode %d: tiles %d, max %d, mean %.1f distinct positions per tile, %d tiles over %d\n", P.method, U, m,
+              gt_geom(m, rowlen, no).ntile, hmax[m], (double)hsum[m] / gt_geom(m, rowlen, no).ntile, hovf[m], GT_MAXENT);
+  int best = -1;
+  static const int force = getenv("IPB_GMODE") ? atoi(getenv("IPB_GMODE")) : -1;
+  for (int m = 0; m < nmode; m++) {
+    if (hmax[m] <= 0) continue;
+    // only the bicubic kernel has a per-tile fallback for lists that do not fit
+    if (hmax[m] > GT_MAXENT && !(P.method == M_BICUBIC && hovf[m] <= gt_geom(m, rowlen, no).ntile / 8)) continue;
+    if (force >= 0 && m != force) continue;
+    if (best < 0 || hsum[m] < hsum[best]) best = m;
+  }
+  if (best >= 0) {
+    T.geom = gt_geom(best, rowlen, no);
+    T.U = U;
+    T.maxent = hmax[best];
+    T.estride = hmax[best] <= GT_PTS ? GT_PTS : 2 * GT_PTS;
+    T.novf = hovf[best];
+    T.esrc = dalloc<int>((size_t)T.geom.ntile * T.estride);
+    T.slot = dalloc<u8>((size_t)U * no);
+    launch(T.geom, 1, T.estride, 3);
+    T.entries = hsum[best];
+    T.bytes = (size_t)T.geom.ntile * T.estride * 4 + (size_t)U * no;
+    T.ok = true;
+  }
+  dfree(d_max); dfree(d_sum);
+}
+
+// ---- apply ---------------------------------------------------------------------------------------------
+enum GtKind { GT_STENCIL = 0, GT_NEIGHBOR = 1, GT_BUDGET = 2 };
+
+template <class R> struct GtArgs {
+  GtGeom g;
+  int estride;
+  const int* esrc;       // [ntile][estride]
+  const u8* slot;        // [U][no]
+  const int* taps;       // [U][no] 1-based source positions (stencil / neighbor: nxy; budget: cn)
+  const R* w;            // [U][no] weights (stencil: wxy; budget: cw)
+  const u8* nc;          // bicubic stencil class per point
+  const R* wsum;         // budget: sum of the sample weights per point
+  int nsamp; const int* bn; const R* bw; const R* wbs;   // budget: the sub-sample plan, for the exact fallback
+};
+
+// One point, one field of the bicubic method from global memory (k_apply_stencil's general path, scalar):
+// incomplete stencils, the bilinear fallback class, bitmaps.
+template <class R>
+__device__ __noinline__ bool bicubic_point_general(const FieldArgs<R>& a, int k, int n, int cls, const int* __restrict__ nxy,
+                                                   const R* __restrict__ wxy, R& og) {
+  const R* __restrict__ g = a.gi + (size_t)k * a.mi;
+  const bool masked = a.ibi[k] != 0;
+  const u8* __restrict__ l = a.li ? a.li + (size_t)k * a.mi : nullptr;
+  R G = 0, W = 0, gmin = DM<R>::huge(), gmax = -DM<R>::huge();
+  if (cls > 0) {
+    for (int t = 0; t < 16; t++) {
+      if (cls == 2) {
+        const int ta = t & 3, tb = t >> 2;
+        if (ta < 1 || ta > 2 || tb < 1 || tb > 2) continue;
+      }
+      const int p = nxy[(size_t)t * a.no + n];
+      if (p > 0 && (!masked || l[p - 1])) {
+        const R w = wxy[(size_t)t * a.no + n], v = g[p - 1];
+        G = G + w * v;
+        W = W + w;
+        if (a.mcon > 0) { gmin = DM<R>::vmin(gmin, v); gmax = DM<R>::vmax(gmax, v); }
+      }
+    }
+  }
+  const bool good = cls > 0 && W >= a.pmp;
+  og = 0;
+  if (good) {
+    og = G / W;
+    if (a.mcon > 0) og = DM<R>::vmin(DM<R>::vmax(og, gmin), gmax);
+  }
+  return good;
+}
+
+// unpredicated 4- / 8-byte asynchronous copy global -> shared
+template <int BYTES> __device__ __forceinline__ void cp_async_b(unsigned smem_addr, const void* gmem) {
+  if (BYTES == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_addr), "l"(gmem));
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_addr), "l"(gmem));
+}
+
+constexpr int GT_MAXKPB = 256;   // fields per block at most (bitmap flags of the block's fields: 8 words)
+
+// NE = staging entries per thread (the tile's list has up to 128*NE positions); MASKED = the batch has
+// fields with a bitmap: the li bytes at the tile's positions are fetched with the values, masked-out values
+// are zeroed in shared memory (w*0 adds nothing, whatever the caller left in a masked-out point) and the
+// usable-tap bits go to shared memory as one byte per position (bit f = field f of the pass).
+template <class R, int U, int KIND, int NE, bool MASKED>
+__global__ void __launch_bounds__(GT_PTS, 4)
+k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
+  constexpr int F = GT_F, ESTR = GT_PTS * NE, BUF = F * ESTR;
+  constexpr int NW = (U + 3) / 4;
+  extern __shared__ __align__(16) unsigned char gt_sm[];
+  R* sm = reinterpret_cast<R*>(gt_sm);                    // [2][F][ESTR] field values at the tile's positions
+  u8* smk = gt_sm + (size_t)2 * BUF * sizeof(R);          // [ESTR] MASKED: bit f = position usable in field f of the pass
+  __shared__ unsigned s_fm[GT_MAXKPB / 32];               // bit j: field k0+j carries a bitmap
+  const int tid = threadIdx.x, r = tid >> 5, lane = tid & 31, tile = blockIdx.x;
+  const int k0 = blockIdx.y * kpb, k1 = min(k0 + kpb, a.kc);
+  if (k0 >= k1) return;
+  const int no = a.no;
+  const int n = gt_point(T.g, tile, r, lane, no);
+  const bool live = n >= 0;
+  const size_t nn = live ? (size_t)n : 0;
+  const size_t mi = (size_t)a.mi;
+  if (a.li) {
+    for (int w = r; w * 32 < k1 - k0; w += GT_PTS / 32) {
+      const int k = k0 + w * 32 + lane;
+      const unsigned b = __ballot_sync(0xffffffffu, k < k1 && a.ibi[k] != 0);
+      if (lane == 0) s_fm[w] = b;
+    }
+    __syncthreads();
+  }
+  auto field_mask = [&](int kb) -> unsigned { return a.li ? (s_fm[(kb - k0) >> 5] >> ((kb - k0) & 31)) & 0xffu : 0u; };
+  // ---- staging assignment: entry q of the tile's sorted list goes to shared-memory slot q ----
+  const int* __restrict__ es = T.esrc + (size_t)tile * T.estride;
+  const bool ovf = es[0] == -2;      // more than 256 distinct positions: this tile gathers from global memory
+  int src[NE];
+  bool act[NE], wact[NE];            // wact: some lane of the warp has an entry (warp-uniform)
+#pragma unroll
+  for (int i = 0; i < NE; i++) {
+    const int s = es[tid + GT_PTS * i];
+    act[i] = s >= 0;
+    src[i] = act[i] ? s : 0;         // lanes without an entry copy position 0 into their own, unused slot
+    wact[i] = __any_sync(0xffffffffu, act[i]);
+  }
+  const unsigned sm_base = (unsigned)__cvta_generic_to_shared(sm);
+  auto stage = [&](int buf, int kb) {
+    const int nf = min(F, k1 - kb);
+#pragma unroll
+    for (int i = 0; i < NE; i++) {
+      if (wact[i]) {
+        const R* __restrict__ gp = a.gi + (size_t)kb * mi + src[i];
+        const unsigned d = sm_base + (unsigned)((buf * BUF + tid + GT_PTS * i) * sizeof(R));
+        if (nf == F) {
+#pragma unroll
+          for (int f = 0; f < F; f++) cp_async_b<sizeof(R)>(d + (unsigned)(f * ESTR * sizeof(R)), gp + (size_t)f * mi);
+        } else {
+          for (int f = 0; f < nf; f++) cp_async_b<sizeof(R)>(d + (unsigned)(f * ESTR * sizeof(R)), gp + (size_t)f * mi);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  u8 mraw[NE][F];
+  auto load_masks = [&](int kb, unsigned m) {   // li bytes of pass kb at this thread's entries
+#pragma unroll
+    for (int i = 0; i < NE; i++) {
+#pragma unroll
+      for (int f = 0; f < F; f++) mraw[i][f] = 1;
+      if (MASKED && m != 0 && wact[i]) {
+        const u8* __restrict__ lp = a.li + (size_t)kb * mi + src[i];
+        if (m == 0xffu) {
+#pragma unroll
+          for (int f = 0; f < F; f++) mraw[i][f] = __ldg(lp + (size_t)f * mi);
+        } else {
+#pragma unroll
+          for (int f = 0; f < F; f++) if ((m >> f) & 1u) mraw[i][f] = __ldg(lp + (size_t)f * mi);
+        }
+      }
+    }
+  };
+  auto fix_masks = [&](int buf) {               // after this thread's own copies of the pass have landed
+#pragma unroll
+    for (int i = 0; i < NE; i++) {
+      if (wact[i]) {
+        unsigned b = 0;
+#pragma unroll
+        for (int f = 0; f < F; f++) b |= (mraw[i][f] ? 1u : 0u) << f;
+        smk[tid + GT_PTS * i] = (u8)b;
+        if (b != 0xffu) {
+#pragma unroll
+          for (int f = 0; f < F; f++) if (!((b >> f) & 1u)) sm[buf * BUF + f * ESTR + tid + GT_PTS * i] = (R)0;
+        }
+      }
+    }
+  };
+  // ---- per-point plan data ----
+  R w[U];
+  unsigned soff[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    soff[u] = (live ? (unsigned)T.slot[(size_t)u * no + nn] : 0u) * (unsigned)sizeof(R);
+    if (KIND == GT_STENCIL && ovf) { const int p = live ? T.taps[(size_t)u * no + nn] : 0; soff[u] = p > 0 ? (unsigned)(p - 1) : 0u; }   // element offset in the field
+    if (KIND != GT_NEIGHBOR) w[u] = live ? T.w[(size_t)u * no + nn] : (R)0; else w[u] = 0;
+  }
+  bool complete = live;       // stencil: the straight-line path applies; neighbor: the point has a source point
+  int cls = 0;
+  R Wall = 0, rWall = 0;      // stencil: weight sum; budget: sample-weight sum and its reciprocal
+  if (KIND == GT_STENCIL) {
+    cls = live ? T.nc[nn] : 0;
+    complete = complete && cls == 1;
+#pragma unroll
+    for (int u = 0; u < U; u++) { complete = complete && (live ? T.taps[(size_t)u * no + nn] : 0) > 0; Wall = Wall + w[u]; }
+    complete = complete && Wall >= a.pmp;
+  } else if (KIND == GT_NEIGHBOR) {
+    complete = live && T.taps[nn] > 0;
+  } else {
+    Wall = live ? T.wsum[nn] : (R)0;
+    rWall = Wall > 0 ? (R)1 / Wall : (R)0;
+  }
+  R* go = a.go + (size_t)k0 * a.mo + nn;
+  u8* lo = a.lo + (size_t)k0 * a.mo + nn;
+  // budget with bitmaps: weight sum of the usable taps, remembered while the usable-tap pattern stays the same
+  unsigned lastp[NW];
+  R wsel = Wall, rsel = rWall;       // the weight sum in force (all taps: the exact sample-weight sum) and its reciprocal
+  bool near_c = false, ones_c = true;
+#pragma unroll
+  for (int q = 0; q < NW; q++) lastp[q] = 0xffffffffu;   // not a pattern (patterns have bits 0, 8, 16, 24 only)
+  // ---- pipeline ----
+  unsigned fm = field_mask(k0);
+  stage(0, k0);
+  if (MASKED) load_masks(k0, fm);
+  int buf = 0;
+  for (int kb = k0; kb < k1; kb += F) {
+    const bool more = kb + F < k1;
+    if (more) stage(buf ^ 1, kb + F);
+    else asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    if (MASKED) {
+      if (fm) fix_masks(buf);
+      if (more) load_masks(kb + F, field_mask(kb + F));
+    }
+    __syncthreads();
+    // ---- compute the pass from shared memory ----
+    const int nf = min(F, k1 - kb);
+    const unsigned char* sb = reinterpret_cast<const unsigned char*>(sm + (size_t)buf * BUF);
+    unsigned mbp[NW];            // per tap one byte, bit f = tap usable in field f of the pass
+    unsigned allm = 0xffu;
+#pragma unroll
+    for (int q = 0; q < NW; q++) mbp[q] = 0;
+    if (MASKED && fm) {
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const unsigned b = live ? (unsigned)smk[soff[u] / (unsigned)sizeof(R)] : 0xffu;
+        mbp[u >> 2] |= b << (8 * (u & 3));
+        allm &= b;
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; u++) mbp[u >> 2] |= 0xffu << (8 * (u & 3));
+    }
+    // The straight-line form of the pass (warp-uniform choice): all F fields present and
+    //   stencil  — every live point of the warp has its complete stencil, no field of the pass has a bitmap;
+    //   neighbor — always (masked-out values are zero in shared memory, lo comes from the usable bits);
+    //   budget   — every field of the pass sees the same usable taps at every point of the warp (then the weight
+    //              sum, its reciprocal and lo are per point and pass, remembered while the pattern stays), and
+    //              no point's weight sum sits next to the threshold.
+    bool fast = nf == F;
+    if (KIND == GT_STENCIL) fast = fast && fm == 0 && __all_sync(0xffffffffu, complete || !live);
+    if (KIND == GT_BUDGET && MASKED && fm) {
+      bool uni = true;
+#pragma unroll
+      for (int q = 0; q < NW; q++) uni = uni && (((mbp[q] ^ (mbp[q] >> 1)) & 0x7f7f7f7fu) == 0);
+      fast = fast && __all_sync(0xffffffffu, uni);
+      if (fast) {
+        bool same = true;
+#pragma unroll
+        for (int q = 0; q < NW; q++) same = same && (mbp[q] & 0x01010101u) == lastp[q];
+        if (!same) {
+          R wo = 0;
+#pragma unroll
+          for (int u = 0; u < U; u++) if ((mbp[u >> 2] >> (8 * (u & 3))) & 1u) wo = wo + w[u];
+          const R d = wo - a.pmp;
+          ones_c = (allm & 1u) != 0;
+          near_c = live && !ones_c && (d < 0 ? -d : d) <= a.pmp * (R)1e-9;
+          wsel = ones_c ? Wall : wo;
+          rsel = ones_c ? rWall : (wo > 0 ? (R)1 / wo : (R)0);
+#pragma unroll
+          for (int q = 0; q < NW; q++) lastp[q] = mbp[q] & 0x01010101u;
+        }
+        fast = !__any_sync(0xffffffffu, near_c);
+      }
+    } else if (KIND == GT_BUDGET) {
+      if (lastp[0] != 0x01010101u || !ones_c) {   // back to "every tap usable"
+        ones_c = true; near_c = false; wsel = Wall; rsel = rWall;
+#pragma unroll
+        for (int q = 0; q < NW; q++) lastp[q] = 0xffffffffu;
+        lastp[0] = 0x01010101u;
+      }
+    }
+    if (fast) {
+      const R* __restrict__ gk = a.gi + (size_t)kb * mi;
+      if (KIND == GT_BUDGET) {
+        const bool good = wsel >= a.pmp;
+        const R rs = rsel;
+#pragma unroll
+        for (int f = 0; f < F; f++) {
+          const unsigned char* sf = sb + (size_t)f * ESTR * sizeof(R);
+          R v[U];
+#pragma unroll
+          for (int u = 0; u < U; u++) v[u] = *reinterpret_cast<const R*>(sf + soff[u]);
+          R acc = 0;   // masked-out values are zero in shared memory: the plain sum is the sum over the usable taps
+#pragma unroll
+          for (int u = 0; u < U; u++) acc = acc + w[u] * v[u];
+          const R og = good ? acc * rs : (R)0;
+          if (live) { __stcs(go, og); __stcs(lo, (u8)(good ? 1 : 0)); }
+          go += a.mo; lo += a.mo;
+        }
+        if (live && !good) for (int f = 0; f < F; f++) mark_bad(a.flag, kb + f);
+      } else if (KIND == GT_STENCIL) {
+#pragma unroll
+        for (int f = 0; f < F; f++) {
+          const unsigned char* sf = sb + (size_t)f * ESTR * sizeof(R);
+          R v[U];
+          if (!ovf) {
+#pragma unroll
+            for (int u = 0; u < U; u++) v[u] = *reinterpret_cast<const R*>(sf + soff[u]);
+          } else {
+#pragma unroll
+            for (int u = 0; u < U; u++) v[u] = __ldg(gk + (size_t)f * mi + soff[u]);
+          }
+          R G = 0;
+#pragma unroll
+          for (int u = 0; u < U; u++) G = G + w[u] * v[u];
+          R og = G / Wall;
+          if (a.mcon > 0) {
+            R gmin = DM<R>::huge(), gmax = -DM<R>::huge();
+#pragma unroll
+            for (int u = 0; u < U; u++) { gmin = DM<R>::vmin(gmin, v[u]); gmax = DM<R>::vmax(gmax, v[u]); }
+            og = DM<R>::vmin(DM<R>::vmax(og, gmin), gmax);
+          }
+          if (live) { __stcs(go, og); __stcs(lo, (u8)1); }
+          go += a.mo; lo += a.mo;
+        }
+      } else {
+#pragma unroll
+        for (int f = 0; f < F; f++) {
+          const unsigned char* sf = sb + (size_t)f * ESTR * sizeof(R);
+          const bool good = complete && ((allm >> f) & 1u);
+          const R og = good ? *reinterpret_cast<const R*>(sf + soff[0]) : (R)0;
+          if (live) { __stcs(go, og); __stcs(lo, (u8)(good ? 1 : 0)); }
+          go += a.mo; lo += a.mo;
+        }
+        if (live && !(complete && allm == 0xffu))
+          for (int f = 0; f < F; f++) if (!(complete && ((allm >> f) & 1u))) mark_bad(a.flag, kb + f);
+      }
+    } else {
+      // general form, per field: ragged last pass, incomplete stencils, bicubic bitmap fields, budget fields that
+      // differ in their usable taps or have a weight sum next to the threshold
+      for (int f = 0; f < nf; f++) {
+        const int k = kb + f;
+        const unsigned char* sf = sb + (size_t)f * ESTR * sizeof(R);
+        R og = 0;
+        bool good = false;
+        if (KIND == GT_STENCIL) {
+          if (complete && !((fm >> f) & 1u)) {
+            R v[U];
+            if (!ovf) {
+#pragma unroll
+              for (int u = 0; u < U; u++) v[u] = *reinterpret_cast<const R*>(sf + soff[u]);
+            } else {
+#pragma unroll
+              for (int u = 0; u < U; u++) v[u] = __ldg(a.gi + (size_t)k * mi + soff[u]);
+            }
+            R G = 0;
+#pragma unroll
+            for (int u = 0; u < U; u++) G = G + w[u] * v[u];
+            og = G / Wall;
+            if (a.mcon > 0) {
+              R gmin = DM<R>::huge(), gmax = -DM<R>::huge();
+#pragma unroll
+              for (int u = 0; u < U; u++) { gmin = DM<R>::vmin(gmin, v[u]); gmax = DM<R>::vmax(gmax, v[u]); }
+              og = DM<R>::vmin(DM<R>::vmax(og, gmin), gmax);
+            }
+            good = true;
+          } else if (live) {
+            good = bicubic_point_general<R>(a, k, n, cls, T.taps, T.w, og);
+          }
+        } else if (KIND == GT_NEIGHBOR) {
+          good = complete && ((allm >> f) & 1u);
+          if (good) og = *reinterpret_cast<const R*>(sf + soff[0]);
+        } else {
+          R v[U];
+#pragma unroll
+          for (int u = 0; u < U; u++) v[u] = *reinterpret_cast<const R*>(sf + soff[u]);
+          R acc = 0, wo = 0;
+#pragma unroll
+          for (int u = 0; u < U; u++) add2_if<R>((mbp[u >> 2] >> (8 * (u & 3) + f)) & 1u, acc, w[u] * v[u], wo, w[u]);
+          if ((allm >> f) & 1u) {
+            good = Wall >= a.pmp;
+            og = good ? acc * rWall : (R)0;
+          } else {
+            const R d = wo - a.pmp;
+            if (live && (d < 0 ? -d : d) <= a.pmp * (R)1e-9) {   // the reference's order and association decide lo
+              acc = budget_exact_point<R>(a.gi + (size_t)k * mi, a.li + (size_t)k * mi, no, n, true, T.nsamp, T.bn, T.bw, T.wbs, wo);
+              good = wo >= a.pmp;
+              og = good ? acc / wo : (R)0;
+            } else {
+              good = wo >= a.pmp;
+              og = good ? acc * (wo > 0 ? (R)1 / wo : (R)0) : (R)0;
+            }
+          }
+        }
+        if (live) {
+          __stcs(go, og);
+          __stcs(lo, (u8)(good ? 1 : 0));
+          if (!good) mark_bad(a.flag, k);
+        }
+        go += a.mo; lo += a.mo;
+      }
+    }
+    __syncthreads();
+    fm = field_mask(kb + F < k1 ? kb + F : k0);
+    buf ^= 1;
+  }
+}
+
+
+template <class R> bool gtiles_ok(const Plan<R>& P, const FieldArgs<R>& a) {
+  if (!P.gt.ok || P.vec) return false;
+  if (P.method == M_BICUBIC) return true;
+  if (P.method == M_NEIGHBOR) return a.mspiral <= 1;
+  if (P.method == M_BUDGET) return budget_collapsed_ok(P, a);
+  return false;
+}
+
+template <class R, int U, int KIND, int NE, bool MASKED>
+void launch_gtiles_inst(const FieldArgs<R>& a, const GtArgs<R>& T, int kpb, cudaStream_t st) {
+  constexpr int SM = 2 * GT_F * GT_PTS * NE * (int)sizeof(R) + (MASKED ? GT_PTS * NE : 0);
+  static bool once = false;
+  if (!once) { IPB_CUDA(cudaFuncSetAttribute(k_gtiles<R, U, KIND, NE, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); once = true; }
+  dim3 grid(T.g.ntile, nblk(a.kc, kpb));
+  k_gtiles<R, U, KIND, NE, MASKED><<<grid, GT_PTS, SM, st>>>(a, T, kpb);
+}
+template <class R, int U, int KIND>
+void launch_gtiles_u(const FieldArgs<R>& a, const GtArgs<R>& T, int kpb, bool masked, cudaStream_t st) {
+  const bool two = T.estride > GT_PTS;
+  if (KIND == GT_STENCIL) masked = false;   // bicubic bitmap fields take the general per-point path
+  if (two) { if (masked) launch_gtiles_inst<R, U, KIND, 2, true>(a, T, kpb, st); else launch_gtiles_inst<R, U, KIND, 2, false>(a, T, kpb, st); }
+  else { if (masked) launch_gtiles_inst<R, U, KIND, 1, true>(a, T, kpb, st); else launch_gtiles_inst<R, U, KIND, 1, false>(a, T, kpb, st); }
+}
+
+template <class R> void launch_gtiles(const Plan<R>& P, const FieldArgs<R>& a, cudaStream_t st) {
+  const GtTables& G = P.gt;
+  GtArgs<R> T;
+  T.g = G.geom; T.estride = G.estride; T.esrc = G.esrc; T.slot = G.slot;
+  T.nc = P.nc; T.wsum = P.cwsum; T.nsamp = P.bo.nsamp; T.bn = P.bn; T.bw = P.bw; T.wbs = P.d_wb;
+  static const int kpb_env = getenv("IPB_GKPB") ? atoi(getenv("IPB_GKPB")) : 64;
+  const int kpb = std::max(GT_F, std::min(GT_MAXKPB, (std::min(a.kc, kpb_env) + GT_F - 1) / GT_F * GT_F));
+  const bool masked = a.li != nullptr;
+  if (P.method == M_BICUBIC) { T.taps = P.nxy; T.w = P.wxy; launch_gtiles_u<R, 16, GT_STENCIL>(a, T, kpb, masked, st); }
+  else if (P.method == M_NEIGHBOR) { T.taps = P.nxy; T.w = nullptr; launch_gtiles_u<R, 1, GT_NEIGHBOR>(a, T, kpb, masked, st); }
+  else {
+    T.taps = P.cn; T.w = P.cw;
+    if constexpr (sizeof(R) == 8) {   // collapsed taps exist in the binary64 kinds only
+      if (G.U == 4) launch_gtiles_u<R, 4, GT_BUDGET>(a, T, kpb, masked, st);
+      else if (G.U == 9) launch_gtiles_u<R, 9, GT_BUDGET>(a, T, kpb, masked, st);
+      else launch_gtiles_u<R, 16, GT_BUDGET>(a, T, kpb, masked, st);
+    }
+  }
+  g_launches++;
+}
+
+}  // namespace ipb

@@ -64,6 +64,17 @@ struct TileTables {
   u8* edst[4] = {nullptr, nullptr, nullptr, nullptr};    // [ntile][cstride] shared-memory slot (cell*4 + tap) of each entry
   size_t bytes = 0;
 };
+// Point-staged kernels (ipb_gtiles.cuh): tile shape and the per-tile lists of distinct source positions.
+struct GtGeom { int mode = 0, rowlen = 0, ntx = 1, ntile = 0; };   // mode 0: 128 consecutive points; 1: 32x4 patch; 2: 16x8 patch
+struct GtTables {
+  bool ok = false;
+  GtGeom geom;
+  int U = 0, estride = 0, maxent = 0, novf = 0;
+  unsigned long long entries = 0;   // distinct positions summed over tiles (= staging copies per field)
+  int* esrc = nullptr;              // [ntile][estride] sorted 0-based source positions, -1 = padding
+  u8* slot = nullptr;               // [U][no] position of every tap in its tile's list
+  size_t bytes = 0;
+};
 struct TileDev { const u8* cid[4]; const int* ncell[4]; const int* cells[4]; const u8* edst[4]; int cstride; int ntile; };
 
 template <class R> struct Plan {
@@ -97,6 +108,7 @@ template <class R> struct Plan {
   // 1-based range of input-field positions any tap refers to (host calls copy only this window)
   int src_lo = 1, src_hi = 0;
   TileTables tiles;
+  GtTables gt;
   R *wq = nullptr, *ws2 = nullptr;   // staged bilinear kernel: weights per point [no][4], (sum, 1/sum) [no][2]
   size_t bytes = 0;
   double build_ms = 0;
@@ -107,6 +119,7 @@ template <class R> struct Plan {
     dfree(pole_n); dfree(pole_s); dfree(pclon_n); dfree(pslon_n); dfree(pclon_s); dfree(pslon_s);
     for (int v = 0; v < 4; v++) { dfree(tiles.cid[v]); dfree(tiles.ncell[v]); dfree(tiles.cells[v]); dfree(tiles.edst[v]); }
     dfree(wq); dfree(ws2);
+    dfree(gt.esrc); dfree(gt.slot);
   }
 };
 
