@@ -1,26 +1,31 @@
 // ipb200 — point-staged apply kernels for the methods whose stencils are not 2x2 cells: bicubic
-// (bicubic_interp_mod.F90:226-272), neighbor (neighbor_interp_mod.F90:213-263) and the collapsed budget
-// taps of the binary64 kinds (budget_interp_mod.F90:252-344 through ipb_budget.cuh).
+// (bicubic_interp_mod.F90:226-272) and the collapsed budget taps of the binary64 kinds
+// (budget_interp_mod.F90:252-344 through ipb_budget.cuh).
 //
 // The general kernels gather every tap of every output point from global memory for every field: 16
-// (bicubic), 9 (+9 bitmap bytes, budget) or 1 (neighbor) scattered loads per point and field, each a
-// handful of 32-byte sectors per warp instruction.  That is what bounds them (L1 tag-stage wavefronts), not
-// HBM.  Here the gathers leave the field loop:
+// (bicubic) or 9 (+9 bitmap bytes, budget) scattered loads per point and field, each a handful of 32-byte
+// sectors per warp instruction.  That is what bounds them (L1 tag-stage wavefronts), not HBM.  Here the
+// gathers leave the field loop:
 //
 //  * the output points are cut into TILES of 128 points — 128 consecutive points, or a 32x4 / 16x8 patch of
-//    the output grid, whichever needs the fewest distinct source points (decided per plan by counting);
+//    the output grid, chosen per plan by counting the distinct source points each shape needs;
 //  * at plan time every tile gets the sorted list of the DISTINCT source positions its points refer to
 //    (at most 256), and every tap of every point the one-byte number ("slot") of its position in that list;
 //  * per pass of 8 fields the block copies those positions from each field into shared memory with
-//    cp.async — address-sorted, so one warp instruction touches few sectors — double buffered, and, for
-//    fields with a bitmap, the li bytes at the same positions packed as one bit per field;
+//    cp.async — address-sorted, so one warp instruction touches few sectors — double buffered; for fields
+//    with a bitmap the li bytes at the same positions come along, masked-out values are zeroed in shared
+//    memory and the usable-tap bits are kept as one byte per position (bit f = field f of the pass);
 //  * the field loop of a thread (one output point) is then U shared-memory loads at precomputed offsets,
 //    the reference's multiply/adds in its order, the division and the go/lo stores — coalesced, 32
-//    consecutive points (or two runs of 16) per warp instruction.
+//    consecutive points (or two runs of 16) per warp instruction.  For budget fields with a bitmap the weight
+//    sum over the usable taps, its reciprocal and lo depend on the point and the bitmap only; they are kept
+//    while consecutive passes show the same usable-tap pattern (the usual case: one land mask for all fields).
 //
-// Arithmetic is the general kernels' (same operations, same order), so results are bit-identical to them.
-// Incomplete stencils, bitmap fields of the bicubic method and near-threshold budget sums take the same
-// general per-point code those kernels use.
+// Arithmetic is the general kernels' (same operations, same order): bicubic results are bit-identical to
+// k_apply_stencil; budget values follow k_budget_collapsed's contract (ipb_budget.cuh: 1e-12, lo bit-exact).
+// Incomplete stencils, bitmap fields of the bicubic method, tiles with more than 256 positions and
+// near-threshold budget sums take the general per-point code inside the same kernel.
+// (The neighbor method was tried on this scheme and stayed with k_neighbor_lane: profiles/README.md.)
 #pragma once
 #include <climits>
 #include <cstdlib>
@@ -138,7 +143,6 @@ template <class R> void build_gtiles(Plan<R>& P, cudaStream_t st) {
   const int* taps = nullptr;
   int U = 0;
   if (P.method == M_BICUBIC && P.nxy) { taps = P.nxy; U = 16; }
-  else if (P.method == M_NEIGHBOR && P.nxy) { taps = P.nxy; U = 1; }
   else if (P.method == M_BUDGET && P.cu > 0 && P.cn) { taps = P.cn; U = P.cu; }
   else return;
   const int no = P.no;
@@ -168,14 +172,20 @@ template <class R> void build_gtiles(Plan<R>& P, cudaStream_t st) {
     for (int m = 0; m < nmode; m++)
       fprintf(stderr, "ipb200: gtiles method %d U %d mode %d: tiles %d, max %d, mean %.1f distinct positions per tile, %d tiles over %d\n", P.method, U, m,
               gt_geom(m, rowlen, no).ntile, hmax[m], (double)hsum[m] / gt_geom(m, rowlen, no).ntile, hovf[m], GT_MAXENT);
+  // Tile shape: fewest staging copies per field, where a tile whose list does not fit (it gathers from global
+  // memory) counts like 2048 copies and the 16x8 patch pays for its short store runs (two 16-point runs per
+  // warp instruction instead of one 32-point run).  Measured on the BASELINE pairs: profiles/README.md.
   int best = -1;
+  double best_cost = 0;
   static const int force = getenv("IPB_GMODE") ? atoi(getenv("IPB_GMODE")) : -1;
   for (int m = 0; m < nmode; m++) {
     if (hmax[m] <= 0) continue;
+    const int nt = gt_geom(m, rowlen, no).ntile;
     // only the bicubic kernel has a per-tile fallback for lists that do not fit
-    if (hmax[m] > GT_MAXENT && !(P.method == M_BICUBIC && hovf[m] <= gt_geom(m, rowlen, no).ntile / 8)) continue;
+    if (hmax[m] > GT_MAXENT && !(P.method == M_BICUBIC && hovf[m] <= nt / 8)) continue;
     if (force >= 0 && m != force) continue;
-    if (best < 0 || hsum[m] < hsum[best]) best = m;
+    const double cost = (double)hsum[m] + 2048.0 * hovf[m] + (m == 2 ? 64.0 * nt : 0.0);
+    if (best < 0 || cost < best_cost) { best = m; best_cost = cost; }
   }
   if (best >= 0) {
     T.geom = gt_geom(best, rowlen, no);
@@ -194,14 +204,14 @@ template <class R> void build_gtiles(Plan<R>& P, cudaStream_t st) {
 }
 
 // ---- apply ---------------------------------------------------------------------------------------------
-enum GtKind { GT_STENCIL = 0, GT_NEIGHBOR = 1, GT_BUDGET = 2 };
+enum GtKind { GT_STENCIL = 0, GT_BUDGET = 2 };
 
 template <class R> struct GtArgs {
   GtGeom g;
   int estride;
   const int* esrc;       // [ntile][estride]
   const u8* slot;        // [U][no]
-  const int* taps;       // [U][no] 1-based source positions (stencil / neighbor: nxy; budget: cn)
+  const int* taps;       // [U][no] 1-based source positions (stencil: nxy; budget: cn)
   const R* w;            // [U][no] weights (stencil: wxy; budget: cw)
   const u8* nc;          // bicubic stencil class per point
   const R* wsum;         // budget: sum of the sample weights per point
@@ -254,7 +264,7 @@ constexpr int GT_MAXKPB = 256;   // fields per block at most (bitmap flags of th
 // are zeroed in shared memory (w*0 adds nothing, whatever the caller left in a masked-out point) and the
 // usable-tap bits go to shared memory as one byte per position (bit f = field f of the pass).
 template <class R, int U, int KIND, int NE, bool MASKED>
-__global__ void __launch_bounds__(GT_PTS, 4)
+__global__ void __launch_bounds__(GT_PTS, (KIND == GT_STENCIL && sizeof(R) == 4) ? 5 : 4)
 k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
   constexpr int F = GT_F, ESTR = GT_PTS * NE, BUF = F * ESTR;
   constexpr int NW = (U + 3) / 4;
@@ -288,7 +298,7 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
   for (int i = 0; i < NE; i++) {
     const int s = es[tid + GT_PTS * i];
     act[i] = s >= 0;
-    src[i] = act[i] ? s : 0;         // lanes without an entry copy position 0 into their own, unused slot
+    src[i] = act[i] ? s : 0;
     wact[i] = __any_sync(0xffffffffu, act[i]);
   }
   const unsigned sm_base = (unsigned)__cvta_generic_to_shared(sm);
@@ -296,7 +306,7 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
     const int nf = min(F, k1 - kb);
 #pragma unroll
     for (int i = 0; i < NE; i++) {
-      if (wact[i]) {
+      if (act[i]) {
         const R* __restrict__ gp = a.gi + (size_t)kb * mi + src[i];
         const unsigned d = sm_base + (unsigned)((buf * BUF + tid + GT_PTS * i) * sizeof(R));
         if (nf == F) {
@@ -349,9 +359,9 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
   for (int u = 0; u < U; u++) {
     soff[u] = (live ? (unsigned)T.slot[(size_t)u * no + nn] : 0u) * (unsigned)sizeof(R);
     if (KIND == GT_STENCIL && ovf) { const int p = live ? T.taps[(size_t)u * no + nn] : 0; soff[u] = p > 0 ? (unsigned)(p - 1) : 0u; }   // element offset in the field
-    if (KIND != GT_NEIGHBOR) w[u] = live ? T.w[(size_t)u * no + nn] : (R)0; else w[u] = 0;
+    w[u] = live ? T.w[(size_t)u * no + nn] : (R)0;
   }
-  bool complete = live;       // stencil: the straight-line path applies; neighbor: the point has a source point
+  bool complete = live;       // stencil: the straight-line path applies
   int cls = 0;
   R Wall = 0, rWall = 0;      // stencil: weight sum; budget: sample-weight sum and its reciprocal
   if (KIND == GT_STENCIL) {
@@ -360,8 +370,6 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
 #pragma unroll
     for (int u = 0; u < U; u++) { complete = complete && (live ? T.taps[(size_t)u * no + nn] : 0) > 0; Wall = Wall + w[u]; }
     complete = complete && Wall >= a.pmp;
-  } else if (KIND == GT_NEIGHBOR) {
-    complete = live && T.taps[nn] > 0;
   } else {
     Wall = live ? T.wsum[nn] : (R)0;
     rWall = Wall > 0 ? (R)1 / Wall : (R)0;
@@ -409,7 +417,6 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
     }
     // The straight-line form of the pass (warp-uniform choice): all F fields present and
     //   stencil  — every live point of the warp has its complete stencil, no field of the pass has a bitmap;
-    //   neighbor — always (masked-out values are zero in shared memory, lo comes from the usable bits);
     //   budget   — every field of the pass sees the same usable taps at every point of the warp (then the weight
     //              sum, its reciprocal and lo are per point and pass, remembered while the pattern stays), and
     //              no point's weight sum sits next to the threshold.
@@ -490,21 +497,11 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
           if (live) { __stcs(go, og); __stcs(lo, (u8)1); }
           go += a.mo; lo += a.mo;
         }
-      } else {
-#pragma unroll
-        for (int f = 0; f < F; f++) {
-          const unsigned char* sf = sb + (size_t)f * ESTR * sizeof(R);
-          const bool good = complete && ((allm >> f) & 1u);
-          const R og = good ? *reinterpret_cast<const R*>(sf + soff[0]) : (R)0;
-          if (live) { __stcs(go, og); __stcs(lo, (u8)(good ? 1 : 0)); }
-          go += a.mo; lo += a.mo;
-        }
-        if (live && !(complete && allm == 0xffu))
-          for (int f = 0; f < F; f++) if (!(complete && ((allm >> f) & 1u))) mark_bad(a.flag, kb + f);
       }
     } else {
       // general form, per field: ragged last pass, incomplete stencils, bicubic bitmap fields, budget fields that
       // differ in their usable taps or have a weight sum next to the threshold
+#pragma unroll 1
       for (int f = 0; f < nf; f++) {
         const int k = kb + f;
         const unsigned char* sf = sb + (size_t)f * ESTR * sizeof(R);
@@ -534,9 +531,6 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
           } else if (live) {
             good = bicubic_point_general<R>(a, k, n, cls, T.taps, T.w, og);
           }
-        } else if (KIND == GT_NEIGHBOR) {
-          good = complete && ((allm >> f) & 1u);
-          if (good) og = *reinterpret_cast<const R*>(sf + soff[0]);
         } else {
           R v[U];
 #pragma unroll
@@ -577,7 +571,6 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
 template <class R> bool gtiles_ok(const Plan<R>& P, const FieldArgs<R>& a) {
   if (!P.gt.ok || P.vec) return false;
   if (P.method == M_BICUBIC) return true;
-  if (P.method == M_NEIGHBOR) return a.mspiral <= 1;
   if (P.method == M_BUDGET) return budget_collapsed_ok(P, a);
   return false;
 }
@@ -603,11 +596,12 @@ template <class R> void launch_gtiles(const Plan<R>& P, const FieldArgs<R>& a, c
   GtArgs<R> T;
   T.g = G.geom; T.estride = G.estride; T.esrc = G.esrc; T.slot = G.slot;
   T.nc = P.nc; T.wsum = P.cwsum; T.nsamp = P.bo.nsamp; T.bn = P.bn; T.bw = P.bw; T.wbs = P.d_wb;
-  static const int kpb_env = getenv("IPB_GKPB") ? atoi(getenv("IPB_GKPB")) : 64;
-  const int kpb = std::max(GT_F, std::min(GT_MAXKPB, (std::min(a.kc, kpb_env) + GT_F - 1) / GT_F * GT_F));
+  // fields per block: the per-point plan data (slots, weights) is re-read once per kpb fields
+  static const int kpb_env = getenv("IPB_GKPB") ? atoi(getenv("IPB_GKPB")) : 0;
+  const int kpb_want = kpb_env > 0 ? kpb_env : (P.method == M_BICUBIC ? 128 : 256);
+  const int kpb = std::max(GT_F, std::min(GT_MAXKPB, (std::min(a.kc, kpb_want) + GT_F - 1) / GT_F * GT_F));
   const bool masked = a.li != nullptr;
   if (P.method == M_BICUBIC) { T.taps = P.nxy; T.w = P.wxy; launch_gtiles_u<R, 16, GT_STENCIL>(a, T, kpb, masked, st); }
-  else if (P.method == M_NEIGHBOR) { T.taps = P.nxy; T.w = nullptr; launch_gtiles_u<R, 1, GT_NEIGHBOR>(a, T, kpb, masked, st); }
   else {
     T.taps = P.cn; T.w = P.cw;
     if constexpr (sizeof(R) == 8) {   // collapsed taps exist in the binary64 kinds only

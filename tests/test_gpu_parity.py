@@ -162,3 +162,55 @@ def test_plan_cache_reuse():
     lib.lib.ipgpu_last_timing(None, None, C.byref(hit))
     assert n1 == 1 and lib.lib.ipgpu_plan_count() == 1 and hit.value == 1
     assert np.array_equal(r1["go"], r2["go"]) and np.array_equal(r1["lo"], r2["lo"])
+
+
+# ---- the point-staged kernels (csrc/ipb_gtiles.cuh): whole passes of 8 fields, bitmap patterns, tile shapes ----
+# (method, ipopt overrides, output grid, km, bitmap pattern)
+#   none: ibi = 0 everywhere; same: every field carries the same bitmap (the usable-tap pattern is remembered);
+#   blocks: the bitmap changes every 8 fields (pattern recomputed per pass); each: a different bitmap per field
+#   (per-field path); mixed: ibi alternates 0/1
+GT_CASES = [(1, {}, "218", 19, "none"), (1, {1: 1}, "8", 17, "mixed"), (1, {}, "203", 16, "none"), (1, {}, "212", 24, "same"),
+            (3, {}, "218", 19, "same"), (3, {}, "218", 24, "blocks"), (3, {}, "212", 17, "none"), (3, {}, "203", 16, "each"),
+            (3, {}, "218", 18, "mixed"), (3, {1: 1, 2: 1, 3: 1, 4: 40}, "212", 16, "same"), (3, {}, "3", 16, "same")]
+
+
+def _gt_case(kind, ip, over, grid, km, pat):
+    gin, gout = ic.g2_input(kind), ic.g2_templates(kind)[grid]
+    mi, mo = ic.npts_of(gin), ic.npts_of(gout)
+    g, _, li = _fields(mi, km, 31 + ip, kind)
+    ibi = [1] * km
+    if pat == "none":
+        ibi = [0] * km
+    elif pat == "mixed":
+        ibi = [(k % 2) for k in range(km)]
+    elif pat == "same":
+        li[:] = li[0]
+    elif pat == "blocks":
+        for k in range(km):
+            li[k] = li[(k // 8) * 8]
+    opt = _ipopt(ip, over)
+    a = product(kind).ipolates(ip, opt, gin, gout, mi, mo, km, ibi, li, g)
+    b = oracle(kind).ipolates(ip, opt, gin, gout, mi, mo, km, ibi, li, g)
+    return assert_same_call(kind, a, b, exact=False, label=f"gt ip{ip} {grid} {pat}")
+
+
+@pytest.mark.parametrize("kind", ["4", "d"])
+@pytest.mark.parametrize("ip,over,grid,km,pat", GT_CASES)
+def test_staged_kernels_vs_oracle(kind, ip, over, grid, km, pat):
+    st = _gt_case(kind, ip, over, grid, km, pat)
+    if ip == 1:   # bicubic: same operations in the same order as the reference
+        assert st[0]["exact_frac"] == 1.0, st
+    print(kind, ip, grid, pat, st)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_staged_kernels_every_tile_shape(mode):
+    """The tile shape is chosen per plan; force each one (read once per process, hence the child process)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, IPB_GMODE=str(mode))
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.join(here, "test_gpu_parity.py"), "-k",
+                        "test_staged_kernels_vs_oracle"], env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
