@@ -28,6 +28,7 @@
 // (The neighbor method was tried on this scheme and stayed with k_neighbor_lane: profiles/README.md.)
 #pragma once
 #include <climits>
+#include <utility>
 #include <cstdlib>
 
 #include "ipb_budget.cuh"
@@ -257,6 +258,21 @@ template <int BYTES> __device__ __forceinline__ void cp_async_b(unsigned smem_ad
   else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_addr), "l"(gmem));
 }
 
+// shared-memory loads by 32-bit shared address: register + compile-time offset, so that a field of the pass costs no
+// address arithmetic (the compiler does not hoist the generic -> shared conversion out of the field loop)
+template <class R, int IMM> __device__ __forceinline__ R lds_at(unsigned addr);
+template <> __device__ __forceinline__ float lds_at<float, 0>(unsigned addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
+template <> __device__ __forceinline__ double lds_at<double, 0>(unsigned addr) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr)); return v; }
+template <class R, int IMM> __device__ __forceinline__ R lds_at(unsigned addr) {
+  R v;
+  if (sizeof(R) == 4) asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(*reinterpret_cast<float*>(&v)) : "r"(addr), "n"(IMM));
+  else asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(*reinterpret_cast<double*>(&v)) : "r"(addr), "n"(IMM));
+  return v;
+}
+
+template <class Fn, int... I> __device__ __forceinline__ void static_for_impl(Fn&& fn, std::integer_sequence<int, I...>) { (fn(std::integral_constant<int, I>{}), ...); }
+template <int N, class Fn> __device__ __forceinline__ void static_for(Fn&& fn) { static_for_impl(fn, std::make_integer_sequence<int, N>{}); }
+
 constexpr int GT_MAXKPB = 256;   // fields per block at most (bitmap flags of the block's fields: 8 words)
 
 // NE = staging entries per thread (the tile's list has up to 128*NE positions); MASKED = the batch has
@@ -357,7 +373,8 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
   unsigned soff[U];
 #pragma unroll
   for (int u = 0; u < U; u++) {
-    soff[u] = (live ? (unsigned)T.slot[(size_t)u * no + nn] : 0u) * (unsigned)sizeof(R);
+    // shared address of the tap in field 0 of the buffer in use (moved from buffer to buffer after every pass)
+    soff[u] = sm_base + (live ? (unsigned)T.slot[(size_t)u * no + nn] : 0u) * (unsigned)sizeof(R);
     if (KIND == GT_STENCIL && ovf) { const int p = live ? T.taps[(size_t)u * no + nn] : 0; soff[u] = p > 0 ? (unsigned)(p - 1) : 0u; }   // element offset in the field
     w[u] = live ? T.w[(size_t)u * no + nn] : (R)0;
   }
@@ -399,7 +416,7 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
     __syncthreads();
     // ---- compute the pass from shared memory ----
     const int nf = min(F, k1 - kb);
-    const unsigned char* sb = reinterpret_cast<const unsigned char*>(sm + (size_t)buf * BUF);
+    const unsigned sbuf = sm_base + (unsigned)(buf * BUF * sizeof(R));
     unsigned mbp[NW];            // per tap one byte, bit f = tap usable in field f of the pass
     unsigned allm = 0xffu;
 #pragma unroll
@@ -407,7 +424,7 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
     if (MASKED && fm) {
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const unsigned b = live ? (unsigned)smk[soff[u] / (unsigned)sizeof(R)] : 0xffu;
+        const unsigned b = live ? (unsigned)smk[(soff[u] - sbuf) / (unsigned)sizeof(R)] : 0xffu;
         mbp[u >> 2] |= b << (8 * (u & 3));
         allm &= b;
       }
@@ -458,28 +475,26 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
       if (KIND == GT_BUDGET) {
         const bool good = wsel >= a.pmp;
         const R rs = rsel;
-#pragma unroll
-        for (int f = 0; f < F; f++) {
-          const unsigned char* sf = sb + (size_t)f * ESTR * sizeof(R);
+        static_for<F>([&](auto fc) {
+          constexpr int f = decltype(fc)::value;
           R v[U];
 #pragma unroll
-          for (int u = 0; u < U; u++) v[u] = *reinterpret_cast<const R*>(sf + soff[u]);
+          for (int u = 0; u < U; u++) v[u] = lds_at<R, f * ESTR * (int)sizeof(R)>(soff[u]);
           R acc = 0;   // masked-out values are zero in shared memory: the plain sum is the sum over the usable taps
 #pragma unroll
           for (int u = 0; u < U; u++) acc = acc + w[u] * v[u];
           const R og = good ? acc * rs : (R)0;
           if (live) { __stcs(go, og); __stcs(lo, (u8)(good ? 1 : 0)); }
           go += a.mo; lo += a.mo;
-        }
+        });
         if (live && !good) for (int f = 0; f < F; f++) mark_bad(a.flag, kb + f);
       } else if (KIND == GT_STENCIL) {
-#pragma unroll
-        for (int f = 0; f < F; f++) {
-          const unsigned char* sf = sb + (size_t)f * ESTR * sizeof(R);
+        static_for<F>([&](auto fc) {
+          constexpr int f = decltype(fc)::value;
           R v[U];
           if (!ovf) {
 #pragma unroll
-            for (int u = 0; u < U; u++) v[u] = *reinterpret_cast<const R*>(sf + soff[u]);
+            for (int u = 0; u < U; u++) v[u] = lds_at<R, f * ESTR * (int)sizeof(R)>(soff[u]);
           } else {
 #pragma unroll
             for (int u = 0; u < U; u++) v[u] = __ldg(gk + (size_t)f * mi + soff[u]);
@@ -496,7 +511,7 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
           }
           if (live) { __stcs(go, og); __stcs(lo, (u8)1); }
           go += a.mo; lo += a.mo;
-        }
+        });
       }
     } else {
       // general form, per field: ragged last pass, incomplete stencils, bicubic bitmap fields, budget fields that
@@ -504,7 +519,7 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
 #pragma unroll 1
       for (int f = 0; f < nf; f++) {
         const int k = kb + f;
-        const unsigned char* sf = sb + (size_t)f * ESTR * sizeof(R);
+        const unsigned fo = (unsigned)(f * ESTR * sizeof(R));
         R og = 0;
         bool good = false;
         if (KIND == GT_STENCIL) {
@@ -512,7 +527,7 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
             R v[U];
             if (!ovf) {
 #pragma unroll
-              for (int u = 0; u < U; u++) v[u] = *reinterpret_cast<const R*>(sf + soff[u]);
+              for (int u = 0; u < U; u++) v[u] = lds_at<R, 0>(soff[u] + fo);
             } else {
 #pragma unroll
               for (int u = 0; u < U; u++) v[u] = __ldg(a.gi + (size_t)k * mi + soff[u]);
@@ -534,7 +549,7 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
         } else {
           R v[U];
 #pragma unroll
-          for (int u = 0; u < U; u++) v[u] = *reinterpret_cast<const R*>(sf + soff[u]);
+          for (int u = 0; u < U; u++) v[u] = lds_at<R, 0>(soff[u] + fo);
           R acc = 0, wo = 0;
 #pragma unroll
           for (int u = 0; u < U; u++) add2_if<R>((mbp[u >> 2] >> (8 * (u & 3) + f)) & 1u, acc, w[u] * v[u], wo, w[u]);
@@ -563,6 +578,10 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
     }
     __syncthreads();
     fm = field_mask(kb + F < k1 ? kb + F : k0);
+    if (!(KIND == GT_STENCIL && ovf)) {
+#pragma unroll
+      for (int u = 0; u < U; u++) soff[u] = buf ? soff[u] - (unsigned)(BUF * sizeof(R)) : soff[u] + (unsigned)(BUF * sizeof(R));
+    }
     buf ^= 1;
   }
 }
