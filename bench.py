@@ -255,6 +255,9 @@ def run_gpu(args, wl):
     lib = pkg.load(kind)
     L = lib.lib
     L.ipgpu_set_device(local)
+    if getattr(args, "chunk_mib", 0) > 0:
+        L.ipgpu_set_chunk_bytes.argtypes = [C.c_longlong]
+        L.ipgpu_set_chunk_bytes(C.c_longlong(args.chunk_mib << 20))
     L.ipgpu_launch_count.restype = C.c_longlong
     L.ipgpu_plan_bytes.restype = C.c_longlong
     L.ipgpu_host_alloc.restype = C.c_void_p
@@ -533,6 +536,7 @@ def main():
     ap.add_argument("--kind", default="", choices=["", "4", "d", "8"], help="build kind override (default: the workload's)")
     ap.add_argument("--mask", type=int, default=-1, help="1: every field carries the land-mask bitmap, 0: none (default: the workload's)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--chunk-mib", type=int, default=0, help="staging size per in-flight chunk of the host-pointer path (default: the library's, 768)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()

@@ -28,6 +28,7 @@
 // (The neighbor method was tried on this scheme and stayed with k_neighbor_lane: profiles/README.md.)
 #pragma once
 #include <climits>
+#include <type_traits>
 #include <utility>
 #include <cstdlib>
 
@@ -259,16 +260,17 @@ template <int BYTES> __device__ __forceinline__ void cp_async_b(unsigned smem_ad
 }
 
 // shared-memory loads by 32-bit shared address: register + compile-time offset, so that a field of the pass costs no
-// address arithmetic (the compiler does not hoist the generic -> shared conversion out of the field loop)
-template <class R, int IMM> __device__ __forceinline__ R lds_at(unsigned addr);
-template <> __device__ __forceinline__ float lds_at<float, 0>(unsigned addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
-template <> __device__ __forceinline__ double lds_at<double, 0>(unsigned addr) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr)); return v; }
+// address arithmetic (the compiler does not hoist the generic -> shared conversion out of the field loop).  The loads
+// are not volatile — the scheduler may interleave the taps of several fields — but their address registers are
+// re-formed after every pass's barrier with a `token` (zero, produced by a volatile asm, opaque to the compiler), so none
+// of them can move above that barrier; their results feed stores that sit before the next one.
 template <class R, int IMM> __device__ __forceinline__ R lds_at(unsigned addr) {
   R v;
-  if (sizeof(R) == 4) asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(*reinterpret_cast<float*>(&v)) : "r"(addr), "n"(IMM));
-  else asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(*reinterpret_cast<double*>(&v)) : "r"(addr), "n"(IMM));
+  if (sizeof(R) == 4) asm("ld.shared.f32 %0, [%1+%2];" : "=f"(*reinterpret_cast<float*>(&v)) : "r"(addr), "n"(IMM));
+  else asm("ld.shared.f64 %0, [%1+%2];" : "=d"(*reinterpret_cast<double*>(&v)) : "r"(addr), "n"(IMM));
   return v;
 }
+__device__ __forceinline__ unsigned pass_token() { unsigned t; asm volatile("mov.u32 %0, 0;" : "=r"(t) :: "memory"); return t; }
 
 template <class Fn, int... I> __device__ __forceinline__ void static_for_impl(Fn&& fn, std::integer_sequence<int, I...>) { (fn(std::integral_constant<int, I>{}), ...); }
 template <int N, class Fn> __device__ __forceinline__ void static_for(Fn&& fn) { static_for_impl(fn, std::make_integer_sequence<int, N>{}); }
@@ -415,6 +417,14 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
     }
     __syncthreads();
     // ---- compute the pass from shared memory ----
+    {
+      // move the tap addresses to this pass's buffer (and make them depend on something produced after the barrier)
+      const unsigned tok = pass_token() + (kb == k0 ? 0u : (buf ? (unsigned)(BUF * sizeof(R)) : 0u - (unsigned)(BUF * sizeof(R))));
+      if (!(KIND == GT_STENCIL && ovf)) {
+#pragma unroll
+        for (int u = 0; u < U; u++) soff[u] += tok;
+      }
+    }
     const int nf = min(F, k1 - kb);
     const unsigned sbuf = sm_base + (unsigned)(buf * BUF * sizeof(R));
     unsigned mbp[NW];            // per tap one byte, bit f = tap usable in field f of the pass
@@ -475,43 +485,60 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
       if (KIND == GT_BUDGET) {
         const bool good = wsel >= a.pmp;
         const R rs = rsel;
-        static_for<F>([&](auto fc) {
-          constexpr int f = decltype(fc)::value;
-          R v[U];
-#pragma unroll
-          for (int u = 0; u < U; u++) v[u] = lds_at<R, f * ESTR * (int)sizeof(R)>(soff[u]);
-          R acc = 0;   // masked-out values are zero in shared memory: the plain sum is the sum over the usable taps
-#pragma unroll
-          for (int u = 0; u < U; u++) acc = acc + w[u] * v[u];
-          const R og = good ? acc * rs : (R)0;
-          if (live) { __stcs(go, og); __stcs(lo, (u8)(good ? 1 : 0)); }
-          go += a.mo; lo += a.mo;
-        });
-        if (live && !good) for (int f = 0; f < F; f++) mark_bad(a.flag, kb + f);
-      } else if (KIND == GT_STENCIL) {
-        static_for<F>([&](auto fc) {
-          constexpr int f = decltype(fc)::value;
-          R v[U];
-          if (!ovf) {
+        // ALL: every lane of the warp has a point (all tiles but those at the grid's edge): unconditional stores,
+        // one basic block for the whole pass, so that the taps of several fields can be in flight together
+        auto pass = [&](auto allc) {
+          constexpr bool ALL = decltype(allc)::value;
+          static_for<F>([&](auto fc) {
+            constexpr int f = decltype(fc)::value;
+            R v[U];
 #pragma unroll
             for (int u = 0; u < U; u++) v[u] = lds_at<R, f * ESTR * (int)sizeof(R)>(soff[u]);
-          } else {
+            R acc = 0;   // masked-out values are zero in shared memory: the plain sum is the sum over the usable taps
 #pragma unroll
-            for (int u = 0; u < U; u++) v[u] = __ldg(gk + (size_t)f * mi + soff[u]);
-          }
-          R G = 0;
+            for (int u = 0; u < U; u++) acc = acc + w[u] * v[u];
+            const R og = good ? acc * rs : (R)0;
+            if (ALL || live) { __stcs(go, og); __stcs(lo, (u8)(good ? 1 : 0)); }
+            go += a.mo; lo += a.mo;
+          });
+        };
+        if (__all_sync(0xffffffffu, live)) pass(std::true_type{}); else pass(std::false_type{});
+        if (live && !good) for (int f = 0; f < F; f++) mark_bad(a.flag, kb + f);
+      } else if (KIND == GT_STENCIL) {
+        // the tap sums of the whole pass first, as one basic block (OVF and CLAMP are compile-time here), so that
+        // the loads of several fields are in flight together; divisions, clamps and stores afterwards
+        auto pass = [&](auto ovfc, auto clampc) {
+          constexpr bool OVF = decltype(ovfc)::value, CLAMP = decltype(clampc)::value;
+          R G[F], gmin[CLAMP ? F : 1], gmax[CLAMP ? F : 1];
+          static_for<F>([&](auto fc) {
+            constexpr int f = decltype(fc)::value;
+            R v[U];
 #pragma unroll
-          for (int u = 0; u < U; u++) G = G + w[u] * v[u];
-          R og = G / Wall;
-          if (a.mcon > 0) {
-            R gmin = DM<R>::huge(), gmax = -DM<R>::huge();
+            for (int u = 0; u < U; u++) {
+              if (!OVF) v[u] = lds_at<R, f * ESTR * (int)sizeof(R)>(soff[u]);
+              else v[u] = __ldg(gk + (size_t)f * mi + soff[u]);
+            }
+            R g = 0;
 #pragma unroll
-            for (int u = 0; u < U; u++) { gmin = DM<R>::vmin(gmin, v[u]); gmax = DM<R>::vmax(gmax, v[u]); }
-            og = DM<R>::vmin(DM<R>::vmax(og, gmin), gmax);
-          }
-          if (live) { __stcs(go, og); __stcs(lo, (u8)1); }
-          go += a.mo; lo += a.mo;
-        });
+            for (int u = 0; u < U; u++) g = g + w[u] * v[u];
+            G[f] = g;
+            if (CLAMP) {
+              R lo_ = DM<R>::huge(), hi_ = -DM<R>::huge();
+#pragma unroll
+              for (int u = 0; u < U; u++) { lo_ = DM<R>::vmin(lo_, v[u]); hi_ = DM<R>::vmax(hi_, v[u]); }
+              gmin[CLAMP ? f : 0] = lo_; gmax[CLAMP ? f : 0] = hi_;
+            }
+          });
+          static_for<F>([&](auto fc) {
+            constexpr int f = decltype(fc)::value;
+            R og = G[f] / Wall;
+            if (CLAMP) og = DM<R>::vmin(DM<R>::vmax(og, gmin[CLAMP ? f : 0]), gmax[CLAMP ? f : 0]);
+            if (live) { __stcs(go, og); __stcs(lo, (u8)1); }
+            go += a.mo; lo += a.mo;
+          });
+        };
+        if (!ovf) { if (a.mcon > 0) pass(std::false_type{}, std::true_type{}); else pass(std::false_type{}, std::false_type{}); }
+        else { if (a.mcon > 0) pass(std::true_type{}, std::true_type{}); else pass(std::true_type{}, std::false_type{}); }
       }
     } else {
       // general form, per field: ragged last pass, incomplete stencils, bicubic bitmap fields, budget fields that
@@ -578,10 +605,6 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
     }
     __syncthreads();
     fm = field_mask(kb + F < k1 ? kb + F : k0);
-    if (!(KIND == GT_STENCIL && ovf)) {
-#pragma unroll
-      for (int u = 0; u < U; u++) soff[u] = buf ? soff[u] - (unsigned)(BUF * sizeof(R)) : soff[u] + (unsigned)(BUF * sizeof(R));
-    }
     buf ^= 1;
   }
 }
