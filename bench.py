@@ -519,8 +519,9 @@ def run_e2e(args, wl, lib, L, torch, dist, dev, world, gin, gout, mi, mo, km, no
     ok = bool(np.array_equal(h_lo[0], lo[0].cpu().numpy())) and bool(np.array_equal(h_go[0].view(np.uint8), go[0].cpu().numpy().view(np.uint8)))
     for p_ in bufs:
         L.ipgpu_host_free(C.c_void_p(p_))
-    return {"value": world * no * kme / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d.value) + kme * 4,
-            "d2h_bytes_per_step": int(d2h.value) + 2 * mo * Rb + kme * 4, "ms_per_step": dt * 1e3, "km_per_gpu": kme, "steps": nstep,
+    # bytes of the whole job (every rank moves the same amount over its own PCIe link)
+    return {"value": world * no * kme / dt, "unit": UNIT, "h2d_bytes_per_step": world * (int(h2d.value) + kme * 4),
+            "d2h_bytes_per_step": world * (int(d2h.value) + 2 * mo * Rb + kme * 4), "ms_per_step": dt * 1e3, "km_per_gpu": kme, "steps": nstep,
             "api": ("ipolatev_grib2_" if vec else "ipolates_grib2_") + wl["kind"] + " (host pointers, pinned; only the source window the plan references is copied in)",
             "matches_device_path": ok}
 
