@@ -387,6 +387,25 @@ def run_gpu(args, wl):
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, burst)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "frac_of_nominal_8TBs": achieved / 8000.0}
 
+    # ---- the alternative north_star names for N > 1: build once, ncclBroadcast the plan ("measure both") --
+    # The plan's arrays stay inside the library; what is timed here is the collective that shipping them would need:
+    # one NCCL broadcast of the plan's byte count from rank 0, against the per-rank rebuild this library does.
+    plan_bcast_ms = None
+    if dist is not None and world > 1:
+        buf = torch.empty(int(plan_bytes), dtype=torch.uint8, device=dev)
+        for _ in range(2):
+            dist.broadcast(buf, src=0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.broadcast(buf, src=0)
+        e1.record()
+        torch.cuda.synchronize()
+        tb = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        plan_bcast_ms = float(tb[0])
+        del buf
+
     # ---- end to end through the host-pointer C ABI (pinned host buffers) --------------------------------
     e2e = None
     if not args.no_e2e:
@@ -423,6 +442,8 @@ def run_gpu(args, wl):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),
             "plan_build_ms": plan_build_ms,
         }
+        if plan_bcast_ms is not None:
+            line["plan_nccl_broadcast_ms_same_bytes"] = plan_bcast_ms
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
