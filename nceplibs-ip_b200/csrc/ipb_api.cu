@@ -23,6 +23,8 @@
 namespace ipb {
 
 std::atomic<long long> g_launches{0};
+bool g_async_alloc = false;
+cudaStream_t g_alloc_stream = nullptr, g_free_stream = nullptr;
 
 #define IPB_CUDA_API(x)                                                                          \
   do {                                                                                           \
@@ -55,6 +57,14 @@ void Runtime::ensure_init() {
     abort();
   }
   for (int i = 0; i < 2; i++) IPB_CUDA_API(cudaStreamCreateWithFlags(&stream[i], cudaStreamNonBlocking));
+  // keep freed plan memory in the pool (stream-ordered allocations of the plan builder, ipb_plan.cuh: dalloc)
+  int devid = 0;
+  cudaMemPool_t pool;
+  if (cudaGetDevice(&devid) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, devid) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    g_free_stream = stream[0];
+  }
   init = true;
 }
 

@@ -47,6 +47,12 @@ template <class R> void cache_put(const std::vector<i64>& key, std::shared_ptr<P
 }
 
 
+// While one of these is alive (always under the runtime mutex) dalloc/dfree are stream-ordered on `s`.
+struct AsyncAlloc {
+  AsyncAlloc(cudaStream_t s) { g_alloc_stream = s; g_async_alloc = true; }
+  ~AsyncAlloc() { g_async_alloc = false; }
+};
+
 // ---- one launch of the apply stage over kc fields already resident on the device ------------------
 template <class R>
 void launch_apply(const Plan<R>& P, bool vec, FieldArgs<R> a, cudaStream_t st) {
@@ -165,6 +171,7 @@ void run(bool vec, int dev, void* user_stream, i64 ip, const i64* ipopt, const G
   RT.last_plan_hit = 0; RT.last_h2d = 0; RT.last_d2h = 0;
   if (!station) { P = cache_find<R>(key); if (P) RT.last_plan_hit = 1; }
   if (!P) {
+    AsyncAlloc scope(st0);   // plan arrays come from the memory pool, ordered on the stream that builds and first uses them
     P.reset(build_plan<R>(method, vec, ipopt, gin, gout, mi, mo, no, rlat, rlon, crot, srot, st0));
     if (P->iret == 0 && !station) { build_tile_tables<R>(*P, st0); P->bytes += P->tiles.bytes; }
     if (P->iret == 0) build_budget_collapse<R>(*P, st0);
@@ -338,6 +345,7 @@ void run_gdswzd(GridHost<R> gh, i64 iopt, i64 npts, R fill, R* x, R* y, R* rlon,
     return;
   }
   cudaStream_t st = RT.stream[0];
+  AsyncAlloc scope(st);
   R* tab = nullptr;
   upload_tables(gh, tab);
   R* out[7] = {crot, srot, xlon, xlat, ylon, ylat, area};

@@ -33,12 +33,28 @@ extern std::atomic<long long> g_launches;  // kernels launched by this library (
     }                                                                                            \
   } while (0)
 
+// Plan arrays are allocated stream-ordered from the device's memory pool while a plan is being built (g_async_alloc
+// set by run(), under the runtime mutex): a plan is ~40 arrays, and cudaMalloc's round trips were most of the 20 ms a
+// first call on a grid pair took; station-point outputs, whose plans are rebuilt on every call, pay it every time.
+extern bool g_async_alloc;
+extern cudaStream_t g_alloc_stream;
 template <class T> T* dalloc(size_t n) {
   T* p = nullptr;
-  IPB_CUDA(cudaMalloc((void**)&p, (n ? n : 1) * sizeof(T)));
+  if (g_async_alloc) IPB_CUDA(cudaMallocAsync((void**)&p, (n ? n : 1) * sizeof(T), g_alloc_stream));
+  else IPB_CUDA(cudaMalloc((void**)&p, (n ? n : 1) * sizeof(T)));
   return p;
 }
-template <class T> void dfree(T*& p) { if (p) cudaFree((void*)p); p = nullptr; }
+// Frees go back to the pool stream-ordered as well: on the building stream while a plan is being built, else on the
+// library's own stream (a plan is only destroyed after every call that used it has synchronised its streams).
+extern cudaStream_t g_free_stream;
+template <class T> void dfree(T*& p) {
+  if (p) {
+    if (g_async_alloc) cudaFreeAsync((void*)p, g_alloc_stream);
+    else if (g_free_stream) cudaFreeAsync((void*)p, g_free_stream);
+    else cudaFree((void*)p);
+  }
+  p = nullptr;
+}
 
 inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
 
@@ -391,9 +407,12 @@ template <class R> void upload_tables(GridHost<R>& gh, R*& dptr) {
   if (gh.p.type != P_GAUSS) return;
   const size_t n = gh.alat.size();
   dptr = dalloc<R>(3 * n);
-  IPB_CUDA(cudaMemcpy(dptr, gh.alat.data(), n * sizeof(R), cudaMemcpyHostToDevice));
-  IPB_CUDA(cudaMemcpy(dptr + n, gh.blat.data(), n * sizeof(R), cudaMemcpyHostToDevice));
-  IPB_CUDA(cudaMemcpy(dptr + 2 * n, gh.ylat_row.data(), n * sizeof(R), cudaMemcpyHostToDevice));
+  // on the allocating stream (the array is stream-ordered); the host vectors are pageable, so each copy has left the
+  // host buffer when the call returns
+  cudaStream_t st = g_async_alloc ? g_alloc_stream : (cudaStream_t)0;
+  IPB_CUDA(cudaMemcpyAsync(dptr, gh.alat.data(), n * sizeof(R), cudaMemcpyHostToDevice, st));
+  IPB_CUDA(cudaMemcpyAsync(dptr + n, gh.blat.data(), n * sizeof(R), cudaMemcpyHostToDevice, st));
+  IPB_CUDA(cudaMemcpyAsync(dptr + 2 * n, gh.ylat_row.data(), n * sizeof(R), cudaMemcpyHostToDevice, st));
   gh.p.alat = dptr; gh.p.blat = dptr + n; gh.p.ylat_row = dptr + 2 * n;
 }
 
