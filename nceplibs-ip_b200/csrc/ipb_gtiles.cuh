@@ -393,6 +393,13 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
     Wall = live ? T.wsum[nn] : (R)0;
     rWall = Wall > 0 ? (R)1 / Wall : (R)0;
   }
+  int utaps = U;              // budget: taps up to the last non-zero weight, maximum over the warp's points
+  if (KIND == GT_BUDGET) {
+    int cnt = 0;
+#pragma unroll
+    for (int u = 0; u < U; u++) if (w[u] != (R)0) cnt = u + 1;
+    utaps = (int)__reduce_max_sync(0xffffffffu, (unsigned)cnt);
+  }
   R* go = a.go + (size_t)k0 * a.mo + nn;
   u8* lo = a.lo + (size_t)k0 * a.mo + nn;
   // budget with bitmaps: weight sum of the usable taps, remembered while the usable-tap pattern stays the same
@@ -486,23 +493,32 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
         const bool good = wsel >= a.pmp;
         const R rs = rsel;
         // ALL: every lane of the warp has a point (all tiles but those at the grid's edge): unconditional stores,
-        // one basic block for the whole pass, so that the taps of several fields can be in flight together
-        auto pass = [&](auto allc) {
+        // one basic block for the whole pass, so that the taps of several fields can be in flight together.
+        // UU: taps actually in use by the warp's points.  The collapsed taps are padded to U with weight zero, and
+        // most points need fewer — 4 when all sub-samples fall into one source cell, 6 when they straddle one cell
+        // edge, 9 at a corner; a sum that stops at the last non-zero weight has the same bits (acc + 0 = acc).
+        auto pass = [&](auto allc, auto uuc) {
           constexpr bool ALL = decltype(allc)::value;
+          constexpr int UU = decltype(uuc)::value < U ? decltype(uuc)::value : U;
           static_for<F>([&](auto fc) {
             constexpr int f = decltype(fc)::value;
-            R v[U];
+            R v[UU];
 #pragma unroll
-            for (int u = 0; u < U; u++) v[u] = lds_at<R, f * ESTR * (int)sizeof(R)>(soff[u]);
+            for (int u = 0; u < UU; u++) v[u] = lds_at<R, f * ESTR * (int)sizeof(R)>(soff[u]);
             R acc = 0;   // masked-out values are zero in shared memory: the plain sum is the sum over the usable taps
 #pragma unroll
-            for (int u = 0; u < U; u++) acc = acc + w[u] * v[u];
+            for (int u = 0; u < UU; u++) acc = acc + w[u] * v[u];
             const R og = good ? acc * rs : (R)0;
             if (ALL || live) { __stcs(go, og); __stcs(lo, (u8)(good ? 1 : 0)); }
             go += a.mo; lo += a.mo;
           });
         };
-        if (__all_sync(0xffffffffu, live)) pass(std::true_type{}); else pass(std::false_type{});
+        const bool all_live = __all_sync(0xffffffffu, live);
+        auto pick = [&](auto uuc) { if (all_live) pass(std::true_type{}, uuc); else pass(std::false_type{}, uuc); };
+        if (U > 4 && utaps <= 4) pick(std::integral_constant<int, 4>{});
+        else if (U > 6 && utaps <= 6) pick(std::integral_constant<int, 6>{});
+        else if (U > 9 && utaps <= 9) pick(std::integral_constant<int, 9>{});
+        else pick(std::integral_constant<int, U>{});
         if (live && !good) for (int f = 0; f < F; f++) mark_bad(a.flag, kb + f);
       } else if (KIND == GT_STENCIL) {
         // the tap sums of the whole pass first, as one basic block (OVF and CLAMP are compile-time here), so that
