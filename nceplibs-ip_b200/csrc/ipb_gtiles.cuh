@@ -281,8 +281,11 @@ constexpr int GT_MAXKPB = 256;   // fields per block at most (bitmap flags of th
 // fields with a bitmap: the li bytes at the tile's positions are fetched with the values, masked-out values
 // are zeroed in shared memory (w*0 adds nothing, whatever the caller left in a masked-out point) and the
 // usable-tap bits go to shared memory as one byte per position (bit f = field f of the pass).
+#ifndef IPB_GT_MINB_BUDGET
+#define IPB_GT_MINB_BUDGET 4
+#endif
 template <class R, int U, int KIND, int NE, bool MASKED>
-__global__ void __launch_bounds__(GT_PTS, (KIND == GT_STENCIL && sizeof(R) == 4) ? 5 : 4)
+__global__ void __launch_bounds__(GT_PTS, KIND == GT_BUDGET ? IPB_GT_MINB_BUDGET : (sizeof(R) == 4 ? 5 : 4))
 k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
   constexpr int F = GT_F, ESTR = GT_PTS * NE, BUF = F * ESTR;
   constexpr int NW = (U + 3) / 4;
