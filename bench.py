@@ -449,10 +449,27 @@ def run_gpu(args, wl):
         }
         if plan_bcast_ms is not None:
             line["plan_nccl_broadcast_ms_same_bytes"] = plan_bcast_ms
+        if world == 1 and args.workload == "bilinear" and not args.no_secondary:
+            line["secondary"] = secondary_budget()
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def secondary_budget():
+    """BASELINE's metric names two workloads ("bilinear+budget"); the line above is the bilinear one.  The budget
+    configuration (ip=3, _d, land-mask bitmap, km=256) is measured right after it in a child process — same code path
+    as `bench.py --workload budget` — and its device-resident numbers are attached under "secondary"."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", "budget", "--steps", "10", "--warmup", "3",
+                            "--no-cpu", "--no-e2e", "--no-secondary"], capture_output=True, text=True, timeout=300)
+        d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+        return {"workload": d["config"]["workload"], "value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"],
+                "dtype": d["dtype"], "steps": d["steps"], "warmup": d["warmup"], "roofline": d["roofline"], "gpu_launches": d["gpu_launches"],
+                "plan_build_ms": d["plan_build_ms"], "plan_rebuild_ms_warm": d.get("plan_rebuild_ms_warm")}
+    except Exception as e:  # the headline line must not depend on it
+        return {"error": repr(e)[:200]}
 
 
 def args_touched(wl):
@@ -563,6 +580,7 @@ def main():
     ap.add_argument("--kind", default="", choices=["", "4", "d", "8"], help="build kind override (default: the workload's)")
     ap.add_argument("--mask", type=int, default=-1, help="1: every field carries the land-mask bitmap, 0: none (default: the workload's)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the budget configuration attached to the default (bilinear) line")
     ap.add_argument("--chunk-mib", type=int, default=0, help="staging size per in-flight chunk of the host-pointer path (default: the library's, 768)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
