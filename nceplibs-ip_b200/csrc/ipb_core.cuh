@@ -175,8 +175,19 @@ void run(bool vec, int dev, void* user_stream, i64 ip, const i64* ipopt, const G
     P.reset(build_plan<R>(method, vec, ipopt, gin, gout, mi, mo, no, rlat, rlon, crot, srot, st0));
     if (P->iret == 0 && !station) { build_tile_tables<R>(*P, st0); P->bytes += P->tiles.bytes; }
     if (P->iret == 0) build_budget_collapse<R>(*P, st0);
-    if (P->iret == 0 && !station) { build_gtiles<R>(*P, st0); P->bytes += P->gt.bytes; }
+    if (P->iret == 0 && !station && method != M_BILINEAR) { build_gtiles<R>(*P, st0); P->bytes += P->gt.bytes; }
     if (!station) cache_put<R>(key, P);
+  }
+  // bilinear calls that carry a bitmap use the point-staged kernel; its tables are added to the plan on first need
+  if (P->iret == 0 && !station && method == M_BILINEAR && !vec && !P->gt.ok && !P->gt_tried && km > 0) {
+    bool anym = false;
+    for (i64 k = 0; k < km; k++) anym = anym || ibi[k] != 0;
+    if (anym) {
+      AsyncAlloc scope(st0);
+      P->gt_tried = true;
+      build_gtiles<R>(*P, st0);
+      P->bytes += P->gt.bytes;
+    }
   }
   cudaEventRecord(t1, st0);
   const int NO = P->no;

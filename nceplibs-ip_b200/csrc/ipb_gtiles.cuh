@@ -145,6 +145,7 @@ template <class R> void build_gtiles(Plan<R>& P, cudaStream_t st) {
   const int* taps = nullptr;
   int U = 0;
   if (P.method == M_BICUBIC && P.nxy) { taps = P.nxy; U = 16; }
+  else if (P.method == M_BILINEAR && P.nxy) { taps = P.nxy; U = 4; }   // built on demand (first call with a bitmap): run()
   else if (P.method == M_BUDGET && P.cu > 0 && P.cn) { taps = P.cn; U = P.cu; }
   else return;
   const int no = P.no;
@@ -206,7 +207,7 @@ template <class R> void build_gtiles(Plan<R>& P, cudaStream_t st) {
 }
 
 // ---- apply ---------------------------------------------------------------------------------------------
-enum GtKind { GT_STENCIL = 0, GT_BUDGET = 2 };
+enum GtKind { GT_STENCIL = 0, GT_BILIN = 1, GT_BUDGET = 2 };   // bicubic; bilinear with bitmaps; collapsed budget
 
 template <class R> struct GtArgs {
   GtGeom g;
@@ -289,6 +290,8 @@ __global__ void __launch_bounds__(GT_PTS, KIND == GT_BUDGET ? IPB_GT_MINB_BUDGET
 k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
   constexpr int F = GT_F, ESTR = GT_PTS * NE, BUF = F * ESTR;
   constexpr int NW = (U + 3) / 4;
+  constexpr bool SUMK = KIND == GT_BUDGET || KIND == GT_BILIN;   // weighted sum over the usable taps, bitmaps from shared memory
+  constexpr bool EXACT = KIND == GT_BILIN;                        // bit-exact contract: IEEE division by the weight sum in tap order
   extern __shared__ __align__(16) unsigned char gt_sm[];
   R* sm = reinterpret_cast<R*>(gt_sm);                    // [2][F][ESTR] field values at the tile's positions
   u8* smk = gt_sm + (size_t)2 * BUF * sizeof(R);          // [ESTR] MASKED: bit f = position usable in field f of the pass
@@ -392,6 +395,11 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
 #pragma unroll
     for (int u = 0; u < U; u++) { complete = complete && (live ? T.taps[(size_t)u * no + nn] : 0) > 0; Wall = Wall + w[u]; }
     complete = complete && Wall >= a.pmp;
+  } else if (KIND == GT_BILIN) {
+    // bilinear_interp_mod.F90:210-219: W accumulates the usable weights in tap order; a missing tap (grid edge) sends
+    // the point to the general per-point code
+#pragma unroll
+    for (int u = 0; u < U; u++) { complete = complete && (live ? T.taps[(size_t)u * no + nn] : 0) > 0; Wall = Wall + w[u]; }
   } else {
     Wall = live ? T.wsum[nn] : (R)0;
     rWall = Wall > 0 ? (R)1 / Wall : (R)0;
@@ -459,7 +467,8 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
     //              no point's weight sum sits next to the threshold.
     bool fast = nf == F;
     if (KIND == GT_STENCIL) fast = fast && fm == 0 && __all_sync(0xffffffffu, complete || !live);
-    if (KIND == GT_BUDGET && MASKED && fm) {
+    if (KIND == GT_BILIN) fast = fast && __all_sync(0xffffffffu, complete || !live);
+    if (SUMK && MASKED && fm) {
       bool uni = true;
 #pragma unroll
       for (int q = 0; q < NW; q++) uni = uni && (((mbp[q] ^ (mbp[q] >> 1)) & 0x7f7f7f7fu) == 0);
@@ -474,7 +483,7 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
           for (int u = 0; u < U; u++) if ((mbp[u >> 2] >> (8 * (u & 3))) & 1u) wo = wo + w[u];
           const R d = wo - a.pmp;
           ones_c = (allm & 1u) != 0;
-          near_c = live && !ones_c && (d < 0 ? -d : d) <= a.pmp * (R)1e-9;
+          near_c = !EXACT && live && !ones_c && (d < 0 ? -d : d) <= a.pmp * (R)1e-9;
           wsel = ones_c ? Wall : wo;
           rsel = ones_c ? rWall : (wo > 0 ? (R)1 / wo : (R)0);
 #pragma unroll
@@ -482,7 +491,7 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
         }
         fast = !__any_sync(0xffffffffu, near_c);
       }
-    } else if (KIND == GT_BUDGET) {
+    } else if (SUMK) {
       if (lastp[0] != 0x01010101u || !ones_c) {   // back to "every tap usable"
         ones_c = true; near_c = false; wsel = Wall; rsel = rWall;
 #pragma unroll
@@ -492,9 +501,9 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
     }
     if (fast) {
       const R* __restrict__ gk = a.gi + (size_t)kb * mi;
-      if (KIND == GT_BUDGET) {
+      if (SUMK) {
         const bool good = wsel >= a.pmp;
-        const R rs = rsel;
+        const R rs = EXACT ? wsel : rsel;   // EXACT divides by the weight sum, budget multiplies by its reciprocal
         // ALL: every lane of the warp has a point (all tiles but those at the grid's edge): unconditional stores,
         // one basic block for the whole pass, so that the taps of several fields can be in flight together.
         // UU: taps actually in use by the warp's points.  The collapsed taps are padded to U with weight zero, and
@@ -511,7 +520,7 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
             R acc = 0;   // masked-out values are zero in shared memory: the plain sum is the sum over the usable taps
 #pragma unroll
             for (int u = 0; u < UU; u++) acc = acc + w[u] * v[u];
-            const R og = good ? acc * rs : (R)0;
+            const R og = good ? (EXACT ? acc / rs : acc * rs) : (R)0;
             if (ALL || live) { __stcs(go, og); __stcs(lo, (u8)(good ? 1 : 0)); }
             go += a.mo; lo += a.mo;
           });
@@ -592,6 +601,26 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
           } else if (live) {
             good = bicubic_point_general<R>(a, k, n, cls, T.taps, T.w, og);
           }
+        } else if (KIND == GT_BILIN) {
+          if (!complete) {
+            if (live) {   // a tap missing at the grid's edge: the reference loop body from global memory
+              if constexpr (U == 4) {
+                int idx[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) idx[u] = T.taps[(size_t)u * no + nn];
+                good = bilinear_point<R>(a.gi + (size_t)k * mi, a.li ? a.li + (size_t)k * mi : nullptr, ((fm >> f) & 1u) != 0, idx, w, a.pmp, og);
+              }
+            }
+          } else {
+            R v[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) v[u] = lds_at<R, 0>(soff[u] + fo);
+            R acc = 0, wo = 0;
+#pragma unroll
+            for (int u = 0; u < U; u++) add2_if<R>((mbp[u >> 2] >> (8 * (u & 3) + f)) & 1u, acc, w[u] * v[u], wo, w[u]);
+            good = wo >= a.pmp;
+            og = good ? acc / wo : (R)0;
+          }
         } else {
           R v[U];
 #pragma unroll
@@ -632,6 +661,7 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
 template <class R> bool gtiles_ok(const Plan<R>& P, const FieldArgs<R>& a) {
   if (!P.gt.ok || P.vec) return false;
   if (P.method == M_BICUBIC) return true;
+  if (P.method == M_BILINEAR) return a.li != nullptr && a.mspiral <= 0;   // batches without a bitmap stay with k_bilinear_tiles
   if (P.method == M_BUDGET) return budget_collapsed_ok(P, a);
   return false;
 }
@@ -639,17 +669,19 @@ template <class R> bool gtiles_ok(const Plan<R>& P, const FieldArgs<R>& a) {
 template <class R, int U, int KIND, int NE, bool MASKED>
 void launch_gtiles_inst(const FieldArgs<R>& a, const GtArgs<R>& T, int kpb, cudaStream_t st) {
   constexpr int SM = 2 * GT_F * GT_PTS * NE * (int)sizeof(R) + (MASKED ? GT_PTS * NE : 0);
-  static bool once = false;
-  if (!once) { IPB_CUDA(cudaFuncSetAttribute(k_gtiles<R, U, KIND, NE, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); once = true; }
+  static_assert(SM <= 48 * 1024, "fits the default dynamic shared-memory limit: no per-device function attribute needed");
   dim3 grid(T.g.ntile, nblk(a.kc, kpb));
   k_gtiles<R, U, KIND, NE, MASKED><<<grid, GT_PTS, SM, st>>>(a, T, kpb);
 }
 template <class R, int U, int KIND>
 void launch_gtiles_u(const FieldArgs<R>& a, const GtArgs<R>& T, int kpb, bool masked, cudaStream_t st) {
   const bool two = T.estride > GT_PTS;
-  if (KIND == GT_STENCIL) masked = false;   // bicubic bitmap fields take the general per-point path
-  if (two) { if (masked) launch_gtiles_inst<R, U, KIND, 2, true>(a, T, kpb, st); else launch_gtiles_inst<R, U, KIND, 2, false>(a, T, kpb, st); }
-  else { if (masked) launch_gtiles_inst<R, U, KIND, 1, true>(a, T, kpb, st); else launch_gtiles_inst<R, U, KIND, 1, false>(a, T, kpb, st); }
+  if constexpr (KIND == GT_STENCIL) {   // bicubic bitmap fields take the general per-point path: no staged bitmap
+    if (two) launch_gtiles_inst<R, U, KIND, 2, false>(a, T, kpb, st); else launch_gtiles_inst<R, U, KIND, 1, false>(a, T, kpb, st);
+  } else {
+    if (two) { if (masked) launch_gtiles_inst<R, U, KIND, 2, true>(a, T, kpb, st); else launch_gtiles_inst<R, U, KIND, 2, false>(a, T, kpb, st); }
+    else { if (masked) launch_gtiles_inst<R, U, KIND, 1, true>(a, T, kpb, st); else launch_gtiles_inst<R, U, KIND, 1, false>(a, T, kpb, st); }
+  }
 }
 
 template <class R> void launch_gtiles(const Plan<R>& P, const FieldArgs<R>& a, cudaStream_t st) {
@@ -659,10 +691,11 @@ template <class R> void launch_gtiles(const Plan<R>& P, const FieldArgs<R>& a, c
   T.nc = P.nc; T.wsum = P.cwsum; T.nsamp = P.bo.nsamp; T.bn = P.bn; T.bw = P.bw; T.wbs = P.d_wb;
   // fields per block: the per-point plan data (slots, weights) is re-read once per kpb fields
   static const int kpb_env = getenv("IPB_GKPB") ? atoi(getenv("IPB_GKPB")) : 0;
-  const int kpb_want = kpb_env > 0 ? kpb_env : (P.method == M_BICUBIC ? 128 : 256);
+  const int kpb_want = kpb_env > 0 ? kpb_env : (P.method == M_BUDGET ? 256 : 128);
   const int kpb = std::max(GT_F, std::min(GT_MAXKPB, (std::min(a.kc, kpb_want) + GT_F - 1) / GT_F * GT_F));
   const bool masked = a.li != nullptr;
   if (P.method == M_BICUBIC) { T.taps = P.nxy; T.w = P.wxy; launch_gtiles_u<R, 16, GT_STENCIL>(a, T, kpb, masked, st); }
+  else if (P.method == M_BILINEAR) { T.taps = P.nxy; T.w = P.wxy; launch_gtiles_u<R, 4, GT_BILIN>(a, T, kpb, masked, st); }
   else {
     T.taps = P.cn; T.w = P.cw;
     if constexpr (sizeof(R) == 8) {   // collapsed taps exist in the binary64 kinds only

@@ -125,6 +125,7 @@ template <class R> struct Plan {
   int src_lo = 1, src_hi = 0;
   TileTables tiles;
   GtTables gt;
+  bool gt_tried = false;   // bilinear: the point-staged tables are built on the first call that carries a bitmap
   R *wq = nullptr, *ws2 = nullptr;   // staged bilinear kernel: weights per point [no][4], (sum, 1/sum) [no][2]
   size_t bytes = 0;
   double build_ms = 0;

@@ -529,8 +529,9 @@ template <class R> void launch_bilinear_tiles(const Plan<R>& P, const FieldArgs<
 #define IPB_TILES_LAUNCH_M(FF, NN, MM)                                                                                    \
   {                                                                                                                       \
     constexpr int SM = TILE_WARPS * (IPB_TILES_NBUF * (FF) * (8 * (NN)) * 4 * (int)sizeof(R) + ((MM) ? (FF) * (8 * (NN)) * 4 : 0)); \
-    static bool once = false;                                                                                             \
-    if (!once) { IPB_CUDA(cudaFuncSetAttribute(k_bilinear_tiles<R, FF, NN, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); once = true; } \
+    static bool once[64] = {};   /* the attribute is per device (ipgpu_set_device may switch within one process) */           \
+    int dv_ = 0; cudaGetDevice(&dv_); dv_ &= 63;                                                                              \
+    if (!once[dv_]) { IPB_CUDA(cudaFuncSetAttribute(k_bilinear_tiles<R, FF, NN, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); once[dv_] = true; } \
     k_bilinear_tiles<R, FF, NN, MM><<<grid, TILE_THREADS, SM, st>>>(a, P.nxy, P.wq, P.ws2, D, base_mis, kpt);              \
   }
 #define IPB_TILES_LAUNCH(FF, NN) { if (a.li) IPB_TILES_LAUNCH_M(FF, NN, true) else IPB_TILES_LAUNCH_M(FF, NN, false) }
