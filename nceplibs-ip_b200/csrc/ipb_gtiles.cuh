@@ -276,6 +276,22 @@ __device__ __forceinline__ unsigned pass_token() { unsigned t; asm volatile("mov
 template <class Fn, int... I> __device__ __forceinline__ void static_for_impl(Fn&& fn, std::integer_sequence<int, I...>) { (fn(std::integral_constant<int, I>{}), ...); }
 template <int N, class Fn> __device__ __forceinline__ void static_for(Fn&& fn) { static_for_impl(fn, std::make_integer_sequence<int, N>{}); }
 
+// num / den with the IEEE quotient's bits, without sending a zero numerator through the division's slow path (FCHK
+// rejects it; masked-out points and fields with exact zeros are full of them): 0 / den = +0 for the den > 0 used here,
+// and the sums formed from +0 are never -0.
+// (the operands are selected in inline asm: the compiler otherwise folds the selects away and divides 0 by 0 again)
+__device__ __forceinline__ float one_unless(float x, bool on) {
+  float r; asm("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n selp.f32 %0, %1, 0f3F800000, p;\n}\n" : "=f"(r) : "f"(x), "r"((unsigned)on)); return r;
+}
+__device__ __forceinline__ double one_unless(double x, bool on) {
+  double r; asm("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n selp.f64 %0, %1, 0d3FF0000000000000, p;\n}\n" : "=d"(r) : "d"(x), "r"((unsigned)on)); return r;
+}
+template <class R> __device__ __forceinline__ R div_or_zero(R num, R den, bool on) {
+  const bool nz = on && num != (R)0;
+  const R q = one_unless(num, nz) / one_unless(den, nz);
+  return nz ? q : (R)0;
+}
+
 constexpr int GT_MAXKPB = 256;   // fields per block at most (bitmap flags of the block's fields: 8 words)
 
 // NE = staging entries per thread (the tile's list has up to 128*NE positions); MASKED = the batch has
@@ -520,7 +536,7 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
             R acc = 0;   // masked-out values are zero in shared memory: the plain sum is the sum over the usable taps
 #pragma unroll
             for (int u = 0; u < UU; u++) acc = acc + w[u] * v[u];
-            const R og = good ? (EXACT ? acc / rs : acc * rs) : (R)0;
+            const R og = EXACT ? div_or_zero<R>(acc, rs, good) : (good ? acc * rs : (R)0);
             if (ALL || live) { __stcs(go, og); __stcs(lo, (u8)(good ? 1 : 0)); }
             go += a.mo; lo += a.mo;
           });
@@ -559,7 +575,7 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
           });
           static_for<F>([&](auto fc) {
             constexpr int f = decltype(fc)::value;
-            R og = G[f] / Wall;
+            R og = div_or_zero<R>(G[f], Wall, true);
             if (CLAMP) og = DM<R>::vmin(DM<R>::vmax(og, gmin[CLAMP ? f : 0]), gmax[CLAMP ? f : 0]);
             if (live) { __stcs(go, og); __stcs(lo, (u8)1); }
             go += a.mo; lo += a.mo;
@@ -619,7 +635,7 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
 #pragma unroll
             for (int u = 0; u < U; u++) add2_if<R>((mbp[u >> 2] >> (8 * (u & 3) + f)) & 1u, acc, w[u] * v[u], wo, w[u]);
             good = wo >= a.pmp;
-            og = good ? acc / wo : (R)0;
+            og = div_or_zero<R>(acc, wo, good);
           }
         } else {
           R v[U];
