@@ -1,6 +1,6 @@
-// ipb200 — point-staged apply kernels for the methods whose stencils are not 2x2 cells: bicubic
-// (bicubic_interp_mod.F90:226-272) and the collapsed budget taps of the binary64 kinds
-// (budget_interp_mod.F90:252-344 through ipb_budget.cuh).
+// ipb200 — point-staged apply kernels: bicubic (bicubic_interp_mod.F90:226-272), the collapsed budget taps of
+// the binary64 kinds (budget_interp_mod.F90:252-344 through ipb_budget.cuh), and bilinear batches that carry
+// bitmaps (bilinear_interp_mod.F90:202-261; batches without one use the cell-staged kernel of ipb_tiles.cuh).
 //
 // The general kernels gather every tap of every output point from global memory for every field: 16
 // (bicubic) or 9 (+9 bitmap bytes, budget) scattered loads per point and field, each a handful of 32-byte
@@ -21,8 +21,9 @@
 //    sum over the usable taps, its reciprocal and lo depend on the point and the bitmap only; they are kept
 //    while consecutive passes show the same usable-tap pattern (the usual case: one land mask for all fields).
 //
-// Arithmetic is the general kernels' (same operations, same order): bicubic results are bit-identical to
-// k_apply_stencil; budget values follow k_budget_collapsed's contract (ipb_budget.cuh: 1e-12, lo bit-exact).
+// Arithmetic is the general kernels' (same operations, same order): bicubic and bilinear results are bit-identical
+// to k_apply_stencil / bilinear_point; budget values follow k_budget_collapsed's contract (ipb_budget.cuh: 1e-12,
+// lo bit-exact).
 // Incomplete stencils, bitmap fields of the bicubic method, tiles with more than 256 positions and
 // near-threshold budget sums take the general per-point code inside the same kernel.
 // (The neighbor method was tried on this scheme and stayed with k_neighbor_lane: profiles/README.md.)
