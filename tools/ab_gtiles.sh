@@ -1,8 +1,14 @@
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "test_staged_kernels_vs_oracle or (scalar_vs_oracle and (4-0 or d-0 or 4-1))" 2>&1 | tail -3
-run() { # args
-  python bench.py --steps 10 --warmup 3 --no-e2e --no-secondary "$@" 2>gpurun_out/bench_x.err | python -c "
+#!/bin/bash
+# A/B of the point-staged kernels against the general ones (profiles/README.md): kernel time per BASELINE configuration
+# with IPB_NO_GTILES=1 and with each tile shape.  Run on a B200:  tools_gpurun.sh 900 "bash tools/ab_gtiles.sh"
+run() { # workload-args... -- env...
+  local args=() ; while [ "$1" != "--" ]; do args+=("$1"); shift; done; shift
+  env "$@" python bench.py "${args[@]}" --steps 10 --warmup 3 --no-cpu --no-e2e --no-secondary 2>/dev/null | python -c "
 import sys, json
-d = json.loads(sys.stdin.readline()); print('$*', 'ms', round(d['roofline']['kernel_ms'],3), 'frac', round(d['roofline']['frac'],3), d['cpu_baseline']['spot_check'])"
+d = json.loads(sys.stdin.readline()); print('${args[*]}', '$*', 'ms', round(d['roofline']['kernel_ms'],3), 'frac', round(d['roofline']['frac'],3))"
 }
-run --workload bilinear --mask 1 --km 256
-run --workload bicubic
+for w in "--workload budget" "--workload bicubic" "--workload bilinear --mask 1 --km 256"; do
+  run $w -- IPB_NO_GTILES=1
+  run $w -- IPB_DEBUG=0
+  for m in 0 1 2; do run $w -- IPB_GMODE=$m; done
+done
