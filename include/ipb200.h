@@ -234,6 +234,10 @@ void ipgpu_last_transfer(long long* h2d_bytes, long long* d2h_bytes); /* field b
 void* ipgpu_host_alloc(long long bytes);          /* pinned host memory (cudaMallocHost) so the host API copies asynchronously */
 void ipgpu_host_free(void* p);
 const char* ipgpu_version(void);
+/* tile geometry of the point-staged kernels (host-side, for tests): mode 0 = 128 consecutive points, 1 = 32 x 4 patch,
+   2 = 16 x 8 patch of an output grid whose rows hold `rowlen` points; the point of (tile, r < 4, lane < 32) or -1 */
+int ipgpu_tile_point(int mode, int rowlen, int no, int tile, int r, int lane);
+int ipgpu_tile_count(int mode, int rowlen, int no);
 
 #ifdef __cplusplus
 }

@@ -7,3 +7,10 @@ template void run<float>(bool, int, void*, i64, const i64*, const GridHost<float
                   const u8*, const float*, const float*, i64&, float*, float*, float*, float*, i64*, u8*, float*, float*, i64&);
 template void run_gdswzd<float>(GridHost<float>, i64, i64, float, float*, float*, float*, float*, i64&, float*, float*, float*, float*, float*, float*, float*);
 }  // namespace ipb
+
+// Host-side view of the point-staged kernels' tile geometry (ipb_gtiles.cuh), for the CPU tests: the output point of
+// (tile, warp row r, lane) for a tile shape, -1 where the tile hangs over the grid; and the number of tiles.
+extern "C" int ipgpu_tile_point(int mode, int rowlen, int no, int tile, int r, int lane) {
+  return ipb::gt_point(ipb::gt_geom(mode, rowlen, no), tile, r, lane, no);
+}
+extern "C" int ipgpu_tile_count(int mode, int rowlen, int no) { return ipb::gt_geom(mode, rowlen, no).ntile; }

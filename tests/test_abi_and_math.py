@@ -79,3 +79,32 @@ def test_libm_sensitivity_of_the_reference_algorithm(grid, ip):
     print(f"grid {grid} ip {ip}: points moved by libm choice > 1e-12: {frac:.3%}, worst {d.max():.3e} (relative to field scale)")
     assert d.max() < 1e-6   # harmless for any user (the reference's ctest tolerance is 1e-4 absolute) ...
     assert np.mean(a["uo"] == b["uo"]) < 1.0   # ... but not bit-reproducible across libms
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("rowlen,no", [(614, 614 * 428), (669, 669 * 1165), (1799, 1799 * 1059), (33, 33 * 5 + 7), (128, 128), (17, 17 * 9)])
+def test_tile_geometry_covers_every_point_once(mode, rowlen, no):
+    """Host logic of the point-staged kernels (csrc/ipb_gtiles.cuh): every output point belongs to exactly one
+    (tile, row, lane) of each tile shape, and nothing outside the grid is addressed."""
+    lib = C.CDLL(pkg.PRODUCT_SO)
+    lib.ipgpu_tile_point.restype = C.c_int
+    lib.ipgpu_tile_count.restype = C.c_int
+    if no > 200000:   # the big grids: check the count, the first and last tiles and a sample in between
+        ntile = lib.ipgpu_tile_count(mode, rowlen, no)
+        tiles = sorted(set([0, 1, ntile - 2, ntile - 1] + list(range(0, ntile, max(1, ntile // 50)))))
+        for t in tiles:
+            pts = [lib.ipgpu_tile_point(mode, rowlen, no, t, r, l) for r in range(4) for l in range(32)]
+            live = [p for p in pts if p >= 0]
+            assert len(live) == len(set(live)) and all(0 <= p < no for p in live)
+        assert ntile * 128 >= no
+        return
+    ntile = lib.ipgpu_tile_count(mode, rowlen, no)
+    seen = np.zeros(no, np.int32)
+    for t in range(ntile):
+        for r in range(4):
+            for l in range(32):
+                p = lib.ipgpu_tile_point(mode, rowlen, no, t, r, l)
+                assert -1 <= p < no
+                if p >= 0:
+                    seen[p] += 1
+    assert seen.min() == 1 and seen.max() == 1
