@@ -387,7 +387,7 @@ def run_gpu(args, wl):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = bpu * no * km / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": load_traffic(args.workload),
+                "traffic": load_traffic(args.workload) if not (args.km or args.kind or args.mask >= 0) else None,   # measured at the workload's own size only
                 "kernel_ms": k_ms, "bytes_per_unit": bpu, "units_per_launch": no * km,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, burst)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "frac_of_nominal_8TBs": achieved / 8000.0}
