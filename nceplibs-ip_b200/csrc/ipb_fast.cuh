@@ -211,11 +211,106 @@ k_neighbor_lane(FieldArgs<R> a, const int* __restrict__ nxy, int kpb, int rowlen
   }
 }
 
+// ---- neighbor, scalar, batches without a bitmap: gather in 8 x 4 sub-patches, store 32-wide --------------------
+// k_neighbor_lane is bound by L1 wavefronts (93 % of peak): a warp of 32 consecutive output points pulls ~15 sectors
+// per gather when the output rows cut across the source rows, on top of the ~6 its two stores cost.  Here a WARP owns
+// a 32 x 4 patch of the output grid, four points per lane.  For the gathers the lane's points are (8s + lane%8,
+// lane/8), s = 0..3: each warp instruction covers an 8 x 4 sub-patch, a compact footprint on the source grid (~6
+// sectors).  The values cross the warp's own shared-memory tile (row pitch 40 words: the four rows of a sub-patch land
+// in distinct banks) and are stored row by row, 32 consecutive points per instruction.  Warps never meet a block
+// barrier; four fields (16 gathers per lane) are in flight, the next round's are issued before this round's stores.
+template <class R>
+__global__ void __launch_bounds__(128)
+k_neighbor_patch(FieldArgs<R> a, const int* __restrict__ nxy, int kpb, int rowlen, int ntx, int npatch) {
+  constexpr int FB = 4, PITCH = 40;
+  __shared__ R tile_all[4][2][FB][4 * PITCH];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int patch = blockIdx.x * 4 + w;
+  if (patch >= npatch) return;
+  R (*tile)[FB][4 * PITCH] = tile_all[w];
+  const int col0 = (patch % ntx) * 32, row0 = (patch / ntx) * 4;
+  int pg[4];                   // gather points: 0-based source position, -1 = none
+  long long ns[4];             // store points: output index, -1 = outside the grid
+  u8 oks[4];
+  bool anybad = false;
+#pragma unroll
+  for (int s = 0; s < 4; s++) {
+    const int gc = col0 + 8 * s + (lane & 7), gr = row0 + (lane >> 3);
+    const long long ng = (long long)gr * rowlen + gc;
+    pg[s] = (gc < rowlen && ng < a.no) ? nxy[ng] - 1 : -1;
+    const int sc = col0 + lane, sr = row0 + s;
+    const long long n = (long long)sr * rowlen + sc;
+    ns[s] = (sc < rowlen && n < a.no) ? n : -1;
+    oks[s] = (ns[s] >= 0 && nxy[ns[s]] > 0) ? 1 : 0;
+    anybad = anybad || (ns[s] >= 0 && !oks[s]);
+  }
+  const int k0 = blockIdx.y * kpb, k1 = min(k0 + kpb, a.kc);
+  if (k0 >= k1) return;
+  const R* __restrict__ g = a.gi + (size_t)k0 * a.mi;
+  R* go = a.go + (size_t)k0 * a.mo;
+  u8* lo = a.lo + (size_t)k0 * a.mo;
+  const int wslot = (lane >> 3) * PITCH + (lane & 7);
+  auto gather = [&](R (&v)[FB][4], int k) {
+#pragma unroll
+    for (int f = 0; f < FB; f++) {
+#pragma unroll
+      for (int s = 0; s < 4; s++) v[f][s] = (pg[s] >= 0 && k + f < k1) ? __ldg(g + (size_t)f * a.mi + pg[s]) : (R)0;
+    }
+  };
+  R v[FB][4], vn[FB][4];
+  gather(v, k0);
+  int buf = 0;
+  for (int k = k0; k < k1; k += FB) {
+#pragma unroll
+    for (int f = 0; f < FB; f++) {
+#pragma unroll
+      for (int s = 0; s < 4; s++) tile[buf][f][wslot + 8 * s] = v[f][s];
+    }
+    g += (size_t)FB * a.mi;
+    if (k + FB < k1) gather(vn, k + FB);     // in flight while this round is stored
+    __syncwarp();
+    const int nf = min(FB, k1 - k);
+#pragma unroll
+    for (int f = 0; f < FB; f++) {
+      if (f < nf) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          if (ns[r] >= 0) {
+            __stcs(go + (size_t)f * a.mo + ns[r], tile[buf][f][r * PITCH + lane]);
+            __stcs(lo + (size_t)f * a.mo + ns[r], oks[r]);
+          }
+        }
+      }
+    }
+    go += (size_t)FB * a.mo; lo += (size_t)FB * a.mo;
+#pragma unroll
+    for (int f = 0; f < FB; f++) {
+#pragma unroll
+      for (int s = 0; s < 4; s++) v[f][s] = vn[f][s];
+    }
+    buf ^= 1;   // the other buffer was last read two rounds ago, before the previous __syncwarp
+  }
+  if (anybad) for (int k = k0; k < k1; k++) mark_bad(a.flag, k);
+}
+
 template <class R> bool fast_neighbor_ok(const Plan<R>& P, const FieldArgs<R>& a) {
   return P.method == M_NEIGHBOR && !P.vec && a.mspiral <= 1 && P.no > 0;
 }
 
 template <class R> void launch_fast_neighbor(const Plan<R>& P, const FieldArgs<R>& a, cudaStream_t st) {
+  static const bool no_patch = getenv("IPB_NPATCH") && atoi(getenv("IPB_NPATCH")) == 0;
+  const GridP<R>& go = P.gout.p;
+  int orow = 0;
+  if (go.type != P_STATION && go.im > 0 && go.jm > 0) orow = go.nscan == 0 ? go.im : go.jm;
+  if (!no_patch && a.li == nullptr && orow >= 32 && orow < a.no) {
+    static const int kpb_env = getenv("IPB_NKPB") ? atoi(getenv("IPB_NKPB")) : 8;   // few fields per block: neighbouring patches of the same fields are written together (measured 8 best: profiles/README.md)
+    const int kpb = std::max(4, std::min(a.kc, kpb_env));
+    const int ntx = nblk(orow, 32), npatch = ntx * nblk(nblk(a.no, orow), 4);
+    dim3 grid(nblk(npatch, 4), nblk(a.kc, kpb));
+    k_neighbor_patch<R><<<grid, 128, 0, st>>>(a, P.nxy, kpb, orow, ntx, npatch);
+    g_launches++;
+    return;
+  }
   // measured on S -> E (km = 1024): plain linear blocks of 256 points with 32 fields per thread are as fast as
   // 32 x 8 patches (2.04 vs 2.25 ms); the patches cut L2 -> SM sectors 4x but the kernel is bound by the
   // scattered first-touch DRAM reads either way
