@@ -303,7 +303,7 @@ template <class R> void launch_fast_neighbor(const Plan<R>& P, const FieldArgs<R
   int orow = 0;
   if (go.type != P_STATION && go.im > 0 && go.jm > 0) orow = go.nscan == 0 ? go.im : go.jm;
   if (!no_patch && a.li == nullptr && orow >= 32 && orow < a.no) {
-    static const int kpb_env = getenv("IPB_NKPB") ? atoi(getenv("IPB_NKPB")) : 8;   // few fields per block: neighbouring patches of the same fields are written together (measured 8 best: profiles/README.md)
+    static const int kpb_env = getenv("IPB_NKPB") ? atoi(getenv("IPB_NKPB")) : 12;   // few fields per block: neighbouring patches of the same fields are written together (measured: 12 best, profiles/README.md)
     const int kpb = std::max(4, std::min(a.kc, kpb_env));
     const int ntx = nblk(orow, 32), npatch = ntx * nblk(nblk(a.no, orow), 4);
     dim3 grid(nblk(npatch, 4), nblk(a.kc, kpb));
