@@ -303,7 +303,9 @@ template <class R> void launch_fast_neighbor(const Plan<R>& P, const FieldArgs<R
   int orow = 0;
   if (go.type != P_STATION && go.im > 0 && go.jm > 0) orow = go.nscan == 0 ? go.im : go.jm;
   if (!no_patch && a.li == nullptr && orow >= 32 && orow < a.no) {
-    static const int kpb_env = getenv("IPB_NKPB") ? atoi(getenv("IPB_NKPB")) : 12;   // few fields per block: neighbouring patches of the same fields are written together (measured: 12 best, profiles/README.md)
+    // few fields per block: the blocks resident together then write neighbouring patches of the same fields
+    // (measured: 12 best, profiles/README.md)
+    static const int kpb_env = getenv("IPB_NKPB") ? atoi(getenv("IPB_NKPB")) : 12;
     const int kpb = std::max(4, std::min(a.kc, kpb_env));
     const int ntx = nblk(orow, 32), npatch = ntx * nblk(nblk(a.no, orow), 4);
     dim3 grid(nblk(npatch, 4), nblk(a.kc, kpb));
@@ -311,9 +313,9 @@ template <class R> void launch_fast_neighbor(const Plan<R>& P, const FieldArgs<R
     g_launches++;
     return;
   }
-  // measured on S -> E (km = 1024): plain linear blocks of 256 points with 32 fields per thread are as fast as
-  // 32 x 8 patches (2.04 vs 2.25 ms); the patches cut L2 -> SM sectors 4x but the kernel is bound by the
-  // scattered first-touch DRAM reads either way
+  // batches with bitmaps, station points: one point per lane.  Measured on S -> E (km = 1024): plain linear blocks of
+  // 256 points with 32 fields per thread are as fast as 32 x 8 patches of one point per lane (2.04 vs 2.25 ms); the
+  // kernel sits at 93 % of the L1TEX wavefront peak (profiles/README.md)
   const int kpb = std::max(1, std::min(a.kc, 32));
   const int rowlen = 256;
   dim3 grid = patch_grid(rowlen, a.no, 8);
