@@ -211,7 +211,7 @@ k_neighbor_lane(FieldArgs<R> a, const int* __restrict__ nxy, int kpb, int rowlen
   }
 }
 
-// ---- neighbor, scalar, batches without a bitmap: gather in 8 x 4 sub-patches, store 32-wide --------------------
+// ---- neighbor, scalar: gather in 8 x 4 sub-patches, store 32-wide ---------------------------------------------
 // k_neighbor_lane is bound by L1 wavefronts (93 % of peak): a warp of 32 consecutive output points pulls ~15 sectors
 // per gather when the output rows cut across the source rows, on top of the ~6 its two stores cost.  Here a WARP owns
 // a 32 x 4 patch of the output grid, four points per lane.  For the gathers the lane's points are (8s + lane%8,
@@ -219,7 +219,9 @@ k_neighbor_lane(FieldArgs<R> a, const int* __restrict__ nxy, int kpb, int rowlen
 // sectors).  The values cross the warp's own shared-memory tile (row pitch 40 words: the four rows of a sub-patch land
 // in distinct banks) and are stored row by row, 32 consecutive points per instruction.  Warps never meet a block
 // barrier; four fields (16 gathers per lane) are in flight, the next round's are issued before this round's stores.
-template <class R>
+// MASKED: the batch has fields with a bitmap; their li bytes are gathered next to the values, in the same sub-patch
+// mapping, and the usable bits travel to the storing lanes by shuffle.
+template <class R, bool MASKED>
 __global__ void __launch_bounds__(128)
 k_neighbor_patch(FieldArgs<R> a, const int* __restrict__ nxy, int kpb, int rowlen, int ntx, int npatch) {
   constexpr int FB = 4, PITCH = 40;
@@ -247,50 +249,72 @@ k_neighbor_patch(FieldArgs<R> a, const int* __restrict__ nxy, int kpb, int rowle
   const int k0 = blockIdx.y * kpb, k1 = min(k0 + kpb, a.kc);
   if (k0 >= k1) return;
   const R* __restrict__ g = a.gi + (size_t)k0 * a.mi;
+  const u8* __restrict__ l = MASKED ? a.li + (size_t)k0 * a.mi : nullptr;
   R* go = a.go + (size_t)k0 * a.mo;
   u8* lo = a.lo + (size_t)k0 * a.mo;
   const int wslot = (lane >> 3) * PITCH + (lane & 7);
-  auto gather = [&](R (&v)[FB][4], int k) {
+  // values (and, MASKED, bitmap bytes: 1 where the field has none) of one round at this lane's gather points
+  auto gather = [&](R (&v)[FB][4], u8 (&m)[FB][4], int k) {
 #pragma unroll
     for (int f = 0; f < FB; f++) {
+      const bool mk = MASKED && k + f < k1 && a.ibi[k + f] != 0;
 #pragma unroll
-      for (int s = 0; s < 4; s++) v[f][s] = (pg[s] >= 0 && k + f < k1) ? __ldg(g + (size_t)f * a.mi + pg[s]) : (R)0;
+      for (int s = 0; s < 4; s++) {
+        const bool on = pg[s] >= 0 && k + f < k1;
+        v[f][s] = on ? __ldg(g + (size_t)f * a.mi + pg[s]) : (R)0;
+        m[f][s] = (MASKED && mk && on) ? __ldg(l + (size_t)f * a.mi + pg[s]) : (u8)1;
+      }
     }
   };
   R v[FB][4], vn[FB][4];
-  gather(v, k0);
+  u8 m[FB][4], mn[FB][4];
+  gather(v, m, k0);
   int buf = 0;
   for (int k = k0; k < k1; k += FB) {
+    unsigned goodbits = 0;     // MASKED: bit 4f+s: this lane's gather point s has a usable source point in field k+f
 #pragma unroll
     for (int f = 0; f < FB; f++) {
 #pragma unroll
-      for (int s = 0; s < 4; s++) tile[buf][f][wslot + 8 * s] = v[f][s];
+      for (int s = 0; s < 4; s++) {
+        const bool ok = pg[s] >= 0 && (!MASKED || m[f][s]);
+        if (MASKED && ok) goodbits |= 1u << (4 * f + s);
+        tile[buf][f][wslot + 8 * s] = (!MASKED || ok) ? v[f][s] : (R)0;
+      }
     }
     g += (size_t)FB * a.mi;
-    if (k + FB < k1) gather(vn, k + FB);     // in flight while this round is stored
+    if (MASKED) l += (size_t)FB * a.mi;
+    if (k + FB < k1) gather(vn, mn, k + FB);     // in flight while this round is stored
     __syncwarp();
     const int nf = min(FB, k1 - k);
+    unsigned gbs[4];           // MASKED: the bits of the lanes that computed this lane's four store points
+#pragma unroll
+    for (int r = 0; r < 4; r++) gbs[r] = MASKED ? __shfl_sync(0xffffffffu, goodbits, r * 8 + (lane & 7)) : 0u;
 #pragma unroll
     for (int f = 0; f < FB; f++) {
       if (f < nf) {
+        bool bad = false;
 #pragma unroll
         for (int r = 0; r < 4; r++) {
           if (ns[r] >= 0) {
+            // store point (row r, column lane) is sub-patch point s = lane/8 of lane r*8 + lane%8
+            const u8 ok = MASKED ? (u8)((gbs[r] >> (4 * f + (lane >> 3))) & 1u) : oks[r];
             __stcs(go + (size_t)f * a.mo + ns[r], tile[buf][f][r * PITCH + lane]);
-            __stcs(lo + (size_t)f * a.mo + ns[r], oks[r]);
+            __stcs(lo + (size_t)f * a.mo + ns[r], ok);
+            bad = bad || !ok;
           }
         }
+        if (MASKED && bad) mark_bad(a.flag, k + f);
       }
     }
     go += (size_t)FB * a.mo; lo += (size_t)FB * a.mo;
 #pragma unroll
     for (int f = 0; f < FB; f++) {
 #pragma unroll
-      for (int s = 0; s < 4; s++) v[f][s] = vn[f][s];
+      for (int s = 0; s < 4; s++) { v[f][s] = vn[f][s]; m[f][s] = mn[f][s]; }
     }
     buf ^= 1;   // the other buffer was last read two rounds ago, before the previous __syncwarp
   }
-  if (anybad) for (int k = k0; k < k1; k++) mark_bad(a.flag, k);
+  if (!MASKED && anybad) for (int k = k0; k < k1; k++) mark_bad(a.flag, k);
 }
 
 template <class R> bool fast_neighbor_ok(const Plan<R>& P, const FieldArgs<R>& a) {
@@ -302,18 +326,19 @@ template <class R> void launch_fast_neighbor(const Plan<R>& P, const FieldArgs<R
   const GridP<R>& go = P.gout.p;
   int orow = 0;
   if (go.type != P_STATION && go.im > 0 && go.jm > 0) orow = go.nscan == 0 ? go.im : go.jm;
-  if (!no_patch && a.li == nullptr && orow >= 32 && orow < a.no) {
+  if (!no_patch && orow >= 32 && orow < a.no) {
     // few fields per block: the blocks resident together then write neighbouring patches of the same fields
     // (measured: 12 best, profiles/README.md)
     static const int kpb_env = getenv("IPB_NKPB") ? atoi(getenv("IPB_NKPB")) : 12;
     const int kpb = std::max(4, std::min(a.kc, kpb_env));
     const int ntx = nblk(orow, 32), npatch = ntx * nblk(nblk(a.no, orow), 4);
     dim3 grid(nblk(npatch, 4), nblk(a.kc, kpb));
-    k_neighbor_patch<R><<<grid, 128, 0, st>>>(a, P.nxy, kpb, orow, ntx, npatch);
+    if (a.li) k_neighbor_patch<R, true><<<grid, 128, 0, st>>>(a, P.nxy, kpb, orow, ntx, npatch);
+    else k_neighbor_patch<R, false><<<grid, 128, 0, st>>>(a, P.nxy, kpb, orow, ntx, npatch);
     g_launches++;
     return;
   }
-  // batches with bitmaps, station points: one point per lane.  Measured on S -> E (km = 1024): plain linear blocks of
+  // station points (no rows to cut patches from): one point per lane.  Measured on S -> E (km = 1024): plain linear blocks of
   // 256 points with 32 fields per thread are as fast as 32 x 8 patches of one point per lane (2.04 vs 2.25 ms); the
   // kernel sits at 93 % of the L1TEX wavefront peak (profiles/README.md)
   const int kpb = std::max(1, std::min(a.kc, 32));
