@@ -171,6 +171,7 @@ def test_plan_cache_reuse():
 #   (per-field path); mixed: ibi alternates 0/1
 GT_CASES = [(0, {}, "218", 19, "same"), (0, {}, "218", 24, "blocks"), (0, {1: 75}, "212", 17, "each"), (0, {}, "203", 16, "mixed"),
             (0, {}, "3", 16, "same"), (0, {}, "127", 9, "same"),
+            (2, {}, "218", 19, "each"), (2, {}, "203", 13, "mixed"), (2, {}, "212", 16, "none"),
             (1, {}, "218", 19, "none"), (1, {1: 1}, "8", 17, "mixed"), (1, {}, "203", 16, "none"), (1, {}, "212", 24, "same"),
             (3, {}, "218", 19, "same"), (3, {}, "218", 24, "blocks"), (3, {}, "212", 17, "none"), (3, {}, "203", 16, "each"),
             (3, {}, "218", 18, "mixed"), (3, {1: 1, 2: 1, 3: 1, 4: 40}, "212", 16, "same"), (3, {}, "3", 16, "same")]
@@ -200,7 +201,7 @@ def _gt_case(kind, ip, over, grid, km, pat):
 @pytest.mark.parametrize("ip,over,grid,km,pat", GT_CASES)
 def test_staged_kernels_vs_oracle(kind, ip, over, grid, km, pat):
     st = _gt_case(kind, ip, over, grid, km, pat)
-    if ip in (0, 1):   # bilinear, bicubic: same operations in the same order as the reference
+    if ip in (0, 1, 2):   # bilinear, bicubic, neighbor: same operations in the same order as the reference
         assert st[0]["exact_frac"] == 1.0, st
     print(kind, ip, grid, pat, st)
 
