@@ -9,6 +9,7 @@
 // default real kind, and in binary64 where the reference uses real64 (the rotated grids).
 #pragma once
 #include <cmath>
+#include <cstdio>
 #include <limits>
 #include <type_traits>
 #include <vector>
@@ -358,6 +359,7 @@ template <class R> GridHost<R> decode_grib2(i64 num, const i64* t, i64 len) {
   GridP<R>& p = gh.p;
   p = GridP<R>();
   p.grid_num = num; p.is_grib2 = 1; p.hi = 1; p.h = 1; p.jh = 1; p.j1 = 1; p.hid = 1;
+  if (len < 0 || len > 65536) { p.type = P_BAD; return gh; }   // not a template length: nothing is read
   gh.key.assign(t, t + len); gh.key.push_back(num); gh.key.push_back(len); gh.key.push_back(2);
   if (num < 0) { p.type = P_STATION; gh.ok = true; return gh; }
   int type;
@@ -371,6 +373,15 @@ template <class R> GridHost<R> decode_grib2(i64 num, const i64* t, i64 len) {
     case 32768: type = P_ROTE; break;
     case 32769: type = P_ROTB; break;
     default: p.type = P_BAD; return gh;  // the reference error-stops here
+  }
+  {  // the template must hold every word this decode reads (the reference would read past the caller's array)
+    static const int need[] = {/*P_EQUID*/ 19, /*P_MERC*/ 19, /*P_LAMBERT*/ 20, /*P_GAUSS*/ 19, /*P_POLAR*/ 18, /*P_ROTB*/ 21, /*P_ROTE*/ 21};
+    int n = 0;
+    switch (type) {
+      case P_EQUID: n = need[0]; break; case P_MERC: n = need[1]; break; case P_LAMBERT: n = need[2]; break;
+      case P_GAUSS: n = need[3]; break; case P_POLAR: n = need[4]; break; case P_ROTB: n = need[5]; break; default: n = need[6];
+    }
+    if (len < n) { fprintf(stderr, "ipb200: grid definition template 3.%lld needs %d words, got %lld\n", (long long)num, n, (long long)len); p.type = P_BAD; return gh; }
   }
   const R micro = IPB_RC(1.0E-6), milli = IPB_RC(1.0E-3);
   const double dprd = (double)K<R>::dpr();

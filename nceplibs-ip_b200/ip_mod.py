@@ -54,9 +54,11 @@ class IpLib:
         k = self._ia(desc[1], 200)
         return [_p(k)], [k]
 
-    def ipolates(self, ip, ipopt, gin, gout, mi, mo, km, ibi, li, gi, no=0, rlat=None, rlon=None, out_init=None):
-        """Returns dict(no, rlat, rlon, ibo, lo, go, iret).  gi: [km, mi] C-order (== Fortran GI(MI,KM))."""
+    def ipolates(self, ip, ipopt, gin, gout, mi, mo, km, ibi, li, gi, no=0, rlat=None, rlon=None, out_init=None, single=False):
+        """Returns dict(no, rlat, rlon, ibo, lo, go, iret).  gi: [km, mi] C-order (== Fortran GI(MI,KM)).
+        single=True calls the *_single_field entry (scalar ibi/ibo, rank-1 fields; src/ipolates.F90:158,808)."""
         assert gin[0] == gout[0]
+        assert not single or km == 1
         R = self.R
         gi = np.ascontiguousarray(gi, dtype=R).reshape(km, mi)
         li = np.ascontiguousarray(li, dtype=np.uint8).reshape(km, mi)
@@ -70,13 +72,16 @@ class IpLib:
         a_in, keep1 = self._grid_args(gin)
         a_out, keep2 = self._grid_args(gout)
         sc = [self._ia([ip]), self._ia(ipopt, 20), self._ia([mi]), self._ia([mo]), self._ia([km]), self._ia(ibi, km)]
-        name = "ipolates_grib2" if gin[0] == "grib2" else "ipolates_grib1"
+        name = ("ipolates_grib2" if gin[0] == "grib2" else "ipolates_grib1") + ("_single_field" if single else "")
         self.fn(name)(_p(sc[0]), _p(sc[1]), *a_in, *a_out, _p(sc[2]), _p(sc[3]), _p(sc[4]), _p(sc[5]), _p(li), _p(gi),
                       _p(no_a), _p(rlat), _p(rlon), _p(ibo), _p(lo), _p(go), _p(iret))
         return dict(no=int(no_a[0]), rlat=rlat, rlon=rlon, ibo=ibo, lo=lo, go=go, iret=int(iret[0]))
 
-    def ipolatev(self, ip, ipopt, gin, gout, mi, mo, km, ibi, li, ui, vi, no=0, rlat=None, rlon=None, crot=None, srot=None):
+    def ipolatev(self, ip, ipopt, gin, gout, mi, mo, km, ibi, li, ui, vi, no=0, rlat=None, rlon=None, crot=None, srot=None,
+                 single=False):
+        """single=True calls the *_single_field entry (src/ipolatev.F90:680,832)."""
         assert gin[0] == gout[0]
+        assert not single or km == 1
         R = self.R
         ui = np.ascontiguousarray(ui, dtype=R).reshape(km, mi)
         vi = np.ascontiguousarray(vi, dtype=R).reshape(km, mi)
@@ -91,7 +96,7 @@ class IpLib:
         a_in, keep1 = self._grid_args(gin)
         a_out, keep2 = self._grid_args(gout)
         sc = [self._ia([ip]), self._ia(ipopt, 20), self._ia([mi]), self._ia([mo]), self._ia([km]), self._ia(ibi, km)]
-        name = "ipolatev_grib2" if gin[0] == "grib2" else "ipolatev_grib1"
+        name = ("ipolatev_grib2" if gin[0] == "grib2" else "ipolatev_grib1") + ("_single_field" if single else "")
         self.fn(name)(_p(sc[0]), _p(sc[1]), *a_in, *a_out, _p(sc[2]), _p(sc[3]), _p(sc[4]), _p(sc[5]), _p(li), _p(ui), _p(vi),
                       _p(no_a), _p(rlat), _p(rlon), _p(crot), _p(srot), _p(ibo), _p(lo), _p(uo), _p(vo), _p(iret))
         return dict(no=int(no_a[0]), rlat=rlat, rlon=rlon, crot=crot, srot=srot, ibo=ibo, lo=lo, uo=uo, vo=vo, iret=int(iret[0]))

@@ -2,12 +2,16 @@
 
 Tolerances are BASELINE.json's: lo / ibo / iret / no and neighbour values bit-exact; interpolated values within
 4 ulp in the _4 kind and 1e-12 relative in _d/_8.  A point whose source coordinate sits within a rounding error
-of a stencil boundary ("projection tie point": binary64 libm of the device vs glibc differ by <= 2 ulp, so a
-floor()/nint() can flip) may pick a different stencil; such points are counted, must be rare, and are reported.
+of a stencil boundary ("projection tie point") could pick a different stencil if the two sides' libm differed;
+both sides use correctly rounded binary64 elementary functions, so there are none: the bar is ZERO lo mismatches
+and ZERO out-of-tolerance values.  Every comparison is logged in RECORDS, any offending point is enumerated
+(index, both values, both lo) and tests/conftest.py dumps the log to gpurun_out/tie_points.json at session end
+(committed copy: profiles/tie_points.json).
 """
 import numpy as np
 
-MAX_TIE_FRACTION = 2e-5  # enumerated tie points allowed per case
+MAX_TIE_FRACTION = 0.0  # no tie points are forgiven; any that appear are enumerated in RECORDS and fail the case
+RECORDS = []            # one entry per compare_fields call of the session
 
 
 def ulp_diff32(a, b):
@@ -18,7 +22,7 @@ def ulp_diff32(a, b):
     return np.abs(ai - bi)
 
 
-def compare_fields(kind, got, ref, lo_g, lo_r, name="go", exact=False):
+def compare_fields(kind, got, ref, lo_g, lo_r, name="go", exact=False, label=""):
     """Returns dict(stats).  Raises AssertionError when outside tolerance."""
     got = np.asarray(got)
     ref = np.asarray(ref)
@@ -43,7 +47,14 @@ def compare_fields(kind, got, ref, lo_g, lo_r, name="go", exact=False):
     nbad = int(bad.sum())
     ties = nbad + lo_mis
     stats = dict(name=name, n=n, lo_mismatch=lo_mis, out_of_tol=nbad, worst=worst, exact_frac=nexact / max(n, 1))
-    assert ties <= max(1, int(MAX_TIE_FRACTION * n)) if ties else True, stats
+    rec = dict(case=str(label), kind=kind, **stats, points=[])
+    if ties:
+        where = np.argwhere(bad | ~both)
+        for idx in where[:64]:
+            t = tuple(int(i) for i in idx)
+            rec["points"].append(dict(index=t, got=float(got[t]), ref=float(ref[t]), lo_got=int(lo_g[t]), lo_ref=int(lo_r[t])))
+    RECORDS.append(rec)
+    assert ties <= int(MAX_TIE_FRACTION * n), rec
     return stats
 
 
@@ -56,10 +67,13 @@ def assert_same_call(kind, a, b, vector=False, exact=False, label=""):
         assert np.array_equal(a["ibo"], b["ibo"]), (label, a["ibo"], b["ibo"])
         names = ("uo", "vo") if vector else ("go",)
         for nm in names:
-            out.append(compare_fields(kind, a[nm], b[nm], a["lo"], b["lo"], nm, exact))
+            out.append(compare_fields(kind, a[nm], b[nm], a["lo"], b["lo"], nm, exact, label))
         for nm in ("rlat", "rlon") + (("crot", "srot") if vector else ()):
-            if kind == "4":
-                assert int(ulp_diff32(a[nm], b[nm]).max(initial=0)) <= 1 or np.mean(a[nm] == b[nm]) > 0.99999, (label, nm)
-            else:
-                assert np.allclose(a[nm], b[nm], rtol=1e-13, atol=1e-11), (label, nm)
+            # geometry comes from the same correctly rounded arithmetic on both sides: bit-identical
+            nd = int((a[nm] != b[nm]).sum())
+            RECORDS.append(dict(case=str(label), kind=kind, name=nm, n=int(a[nm].size), lo_mismatch=0, out_of_tol=nd, worst=0,
+                                exact_frac=1.0 - nd / max(a[nm].size, 1),
+                                points=[dict(index=(int(i),), got=float(a[nm][i]), ref=float(b[nm][i]), lo_got=1, lo_ref=1)
+                                        for i in np.flatnonzero(a[nm] != b[nm])[:64]]))
+            assert nd == 0, (label, nm, nd)
     return out
