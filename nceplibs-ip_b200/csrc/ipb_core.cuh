@@ -13,6 +13,7 @@
 #include "ipb_tiles.cuh"
 #include "ipb_budget.cuh"
 #include "ipb_gtiles.cuh"
+#include "ipb_box.cuh"
 #include "ipb_state.h"
 
 namespace ipb {
@@ -62,6 +63,7 @@ void launch_apply(const Plan<R>& P, bool vec, FieldArgs<R> a, cudaStream_t st) {
   const int method = P.method;
   if (gtiles_ok(P, a)) { launch_gtiles(P, a, st); return; }
   if (method == M_BILINEAR || method == M_BICUBIC) {
+    if (method == M_BILINEAR && !vec && box_ok(P, a) && launch_bilinear_box(P, a, st)) return;
     if (method == M_BILINEAR && !vec && tiles_ok(P, a)) { launch_bilinear_tiles(P, a, st); return; }
     if (method == M_BILINEAR && !vec && fast_bilinear_ok(P, a)) { launch_fast_bilinear(P, a, st); return; }
     const int kpb = std::max(1, std::min(a.kc, 64));   // fields per thread: the plan entry is re-read once per kpb fields
@@ -173,7 +175,7 @@ void run(bool vec, int dev, void* user_stream, i64 ip, const i64* ipopt, const G
   if (!P) {
     AsyncAlloc scope(st0);   // plan arrays come from the memory pool, ordered on the stream that builds and first uses them
     P.reset(build_plan<R>(method, vec, ipopt, gin, gout, mi, mo, no, rlat, rlon, crot, srot, st0));
-    if (P->iret == 0 && !station) { build_tile_tables<R>(*P, st0); P->bytes += P->tiles.bytes; }
+    if (P->iret == 0 && !station) { build_tile_tables<R>(*P, st0); P->bytes += P->tiles.bytes; build_box_tables<R>(*P, st0); }
     if (P->iret == 0) build_budget_collapse<R>(*P, st0);
     if (P->iret == 0 && !station && method != M_BILINEAR) { build_gtiles<R>(*P, st0); P->bytes += P->gt.bytes; }
     if (!station) cache_put<R>(key, P);

@@ -127,6 +127,9 @@ template <class R> struct Plan {
   GtTables gt;
   bool gt_tried = false;   // bilinear: the point-staged tables are built on the first call that carries a bitmap
   R *wq = nullptr, *ws2 = nullptr;   // staged bilinear kernel: weights per point [no][4], (sum, 1/sum) [no][2]
+  bool box_ok = false;               // TMA-staged bilinear kernel (ipb_box.cuh)
+  double box_wmin = 0;               // smallest weight sum over the existing taps of any point (lo = 1 everywhere iff >= pmp)
+  int* bxy = nullptr;                // [no] source cell of every point (iy << 16 | ix), -1 = irregular stencil
   size_t bytes = 0;
   double build_ms = 0;
 
@@ -135,7 +138,7 @@ template <class R> struct Plan {
     dfree(nxy); dfree(wxy); dfree(cxy); dfree(sxy); dfree(nc); dfree(bn); dfree(bw); dfree(bc); dfree(bs); dfree(d_wb); dfree(cn); dfree(cw); dfree(cwsum);
     dfree(pole_n); dfree(pole_s); dfree(pclon_n); dfree(pslon_n); dfree(pclon_s); dfree(pslon_s);
     for (int v = 0; v < 4; v++) { dfree(tiles.cid[v]); dfree(tiles.ncell[v]); dfree(tiles.cells[v]); dfree(tiles.edst[v]); }
-    dfree(wq); dfree(ws2);
+    dfree(wq); dfree(ws2); dfree(bxy);
     dfree(gt.esrc); dfree(gt.slot);
   }
 };

@@ -1,0 +1,14 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+run() { local label="$1"; shift; local out
+  out=$(env "$@" python bench.py --steps 20 --warmup 3 --no-cpu --no-e2e --no-secondary $EXTRA 2>/dev/null | tail -1)
+  echo "$label $(echo "$out" | python -c 'import sys,json; d=json.loads(sys.stdin.read()); print("ms_per_step=%.4f kernel_ms=%.4f frac=%.3f" % (d["ms_per_step"], d["roofline"]["kernel_ms"], d["roofline"]["frac"]))' 2>/dev/null || echo "FAILED: $out")"; }
+EXTRA="$*"
+for mb in 4 5 6; do
+run "align=64 kpt=64 minb=$mb" IPB_BOX_ALIGN=64 IPB_BOX_KPT=64 IPB_BOX_MINB=$mb
+done
+run "align=32 kpt=64 minb=5" IPB_BOX_ALIGN=32 IPB_BOX_KPT=64 IPB_BOX_MINB=5
+run "align=32 kpt=128 minb=5" IPB_BOX_ALIGN=32 IPB_BOX_KPT=128 IPB_BOX_MINB=5
+run "align=16 kpt=256 minb=5" IPB_BOX_ALIGN=16 IPB_BOX_KPT=256 IPB_BOX_MINB=5
+run "align=16 kpt=128 minb=5" IPB_BOX_ALIGN=16 IPB_BOX_KPT=128 IPB_BOX_MINB=5
+run "align=64 kpt=64 minb=6 nr=2" IPB_BOX_ALIGN=64 IPB_BOX_KPT=64 IPB_BOX_NR=2

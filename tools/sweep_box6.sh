@@ -1,0 +1,12 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+run() { local label="$1"; shift; local out
+  out=$(env "$@" python bench.py --steps 20 --warmup 3 --no-cpu --no-e2e --no-secondary $EXTRA 2>/dev/null | tail -1)
+  echo "$label $(echo "$out" | python -c 'import sys,json; d=json.loads(sys.stdin.read()); print("ms_per_step=%.4f kernel_ms=%.4f frac=%.3f" % (d["ms_per_step"], d["roofline"]["kernel_ms"], d["roofline"]["frac"]))' 2>/dev/null || echo "FAILED: $out")"; }
+EXTRA="$*"
+for mb in 4 5 6; do run "w=4 minb=$mb" IPB_BOX_MINB=$mb; done
+for mb in 2 3; do run "w=8 minb=$mb" IPB_BOX_WARPS=8 IPB_BOX_MINB=$mb; done
+run "w=4 minb=5 kpt=16" IPB_BOX_KPT=16
+run "w=4 minb=6 align=64 kpt=64" IPB_BOX_MINB=6 IPB_BOX_ALIGN=64 IPB_BOX_KPT=64
+run "w=4 minb=6 align=64 kpt=32" IPB_BOX_MINB=6 IPB_BOX_ALIGN=64 IPB_BOX_KPT=32
+run "w=4 minb=5 align=64 kpt=64" IPB_BOX_MINB=5 IPB_BOX_ALIGN=64 IPB_BOX_KPT=64
