@@ -13,7 +13,8 @@
  * In/out conventions, iret codes (0 ok, 2 no overlap, 3 bad output grid / mo too small, 32 bad ipopt) and
  * the option words are the reference's (docs in src/ipolates.F90:337-586, src/ipolatev.F90:122-381).
  * Additional codes produced only by this library: iret = 1 for a grid template or method it does not
- * implement (the reference error-stops), iret = 1000 + cudaError for a CUDA failure.
+ * implement or a template shorter than its decode needs (the reference error-stops / reads past the array),
+ * iret = 1000 + cudaError for a CUDA failure, iret = 1001 for a host-side failure (out of memory).
  * ip = 4 (spectral) is out of scope.  There is no CPU fallback: without a CUDA device the library aborts.
  *
  * The *_single_field entry points take scalar ibi / ibo and rank-1 li, gi, lo, go; km is ignored (1).
@@ -79,10 +80,11 @@ void gdswzd_grib1_4(
     const int32_t* kgds, int32_t iopt, int32_t npts, float fill,
     float* xpts, float* ypts, float* rlon, float* rlat, int32_t* nret,
     float* crot, float* srot, float* xlon, float* xlat, float* ylon, float* ylat, float* area);
-/* Device-resident variants (new): li, gi/ui/vi, lo, go/uo/vo are DEVICE pointers and so are
- * rlat, rlon, crot, srot (each may be NULL to skip that output; for station-point outputs they are inputs).
- * Scalars, ipopt, the grid definition, ibi, ibo, no and iret stay host memory.  Work is queued on `stream`
- * (a cudaStream_t) and the call returns after that stream has drained. */
+/* Device-resident variants (new): li, gi/ui/vi, lo, go/uo/vo are DEVICE pointers (on the calling
+ * thread's current device) and so are rlat, rlon, crot, srot (each may be NULL to skip that output; for station-point
+ * outputs they are inputs).  Scalars, ipopt, the grid definition, ibi, ibo, no and iret stay host memory.  Work is queued
+ * on `stream` (a cudaStream_t) and the call returns after that stream has drained (ibo is a host output); the
+ * ipgpu_plan_* entry points below queue without waiting. */
 void ipgpu_ipolates_grib2_dev_4(
     void* stream, const int32_t* ip, const int32_t* ipopt, const int32_t* igdtnumi, const int32_t* igdtmpli, const int32_t* igdtleni, const int32_t* igdtnumo, const int32_t* igdtmplo, const int32_t* igdtleno,
     const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const float* gi,
@@ -91,6 +93,29 @@ void ipgpu_ipolatev_grib2_dev_4(
     void* stream, const int32_t* ip, const int32_t* ipopt, const int32_t* igdtnumi, const int32_t* igdtmpli, const int32_t* igdtleni, const int32_t* igdtnumo, const int32_t* igdtmplo, const int32_t* igdtleno,
     const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const float* ui, const float* vi,
     int32_t* no, float* rlat, float* rlon, float* crot, float* srot, int32_t* ibo, ipb_bool* lo, float* uo, float* vo, int32_t* iret);
+/* the same for the GRIB1 interface (kgds arrays of 200 words) */
+void ipgpu_ipolates_grib1_dev_4(
+    void* stream, const int32_t* ip, const int32_t* ipopt, const int32_t* kgdsi, const int32_t* kgdso,
+    const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const float* gi,
+    int32_t* no, float* rlat, float* rlon, int32_t* ibo, ipb_bool* lo, float* go, int32_t* iret);
+void ipgpu_ipolatev_grib1_dev_4(
+    void* stream, const int32_t* ip, const int32_t* ipopt, const int32_t* kgdsi, const int32_t* kgdso,
+    const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const float* ui, const float* vi,
+    int32_t* no, float* rlat, float* rlon, float* crot, float* srot, int32_t* ibo, ipb_bool* lo, float* uo, float* vo, int32_t* iret);
+/* Explicit plan handles.  ipgpu_plan_get builds the plan of (grid in, grid out, ip, ipopt) on the
+ * current device or fetches it from that device's cache and returns a handle (NULL on failure: iret as ipolates gives it;
+ * station-point outputs have no cacheable plan).  *vector != 0 asks for the ipolatev plan.  ipgpu_plan_apply queues the
+ * km-field apply stage on `stream` (a cudaStream_t) and RETURNS WITHOUT WAITING: li, gi/ui, vi (NULL for scalars), lo,
+ * go/uo, vo are device pointers; ibi is read from the host before the call returns; ibo_dev (km int32 on the device, may
+ * be NULL) receives ibo when the stream gets there.  ipgpu_plan_geometry copies rlat/rlon(/crot/srot) to host or device
+ * arrays (any may be NULL), queued on `stream`.  Release every handle with ipgpu_plan_release. */
+void* ipgpu_plan_get_4(
+    const int32_t* vector, const int32_t* ip, const int32_t* ipopt, const int32_t* igdtnumi, const int32_t* igdtmpli, const int32_t* igdtleni, const int32_t* igdtnumo, const int32_t* igdtmplo, const int32_t* igdtleno,
+    const int32_t* mi, const int32_t* mo, int32_t* no, int32_t* iret);
+void ipgpu_plan_geometry_4(void* plan, void* stream, float* rlat, float* rlon, float* crot, float* srot, int32_t* iret);
+void ipgpu_plan_apply_4(
+    void* plan, void* stream, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const float* gi, const float* vi,
+    int32_t* ibo_dev, ipb_bool* lo, float* go, float* vo, int32_t* iret);
 
 /* ======================== kind _d  (libip_d: INTEGER(4), REAL(8)) ======================== */
 /* replaces ipolates_grib2, src/ipolates.F90:587-636 */
@@ -143,10 +168,11 @@ void gdswzd_grib1_d(
     const int32_t* kgds, int32_t iopt, int32_t npts, double fill,
     double* xpts, double* ypts, double* rlon, double* rlat, int32_t* nret,
     double* crot, double* srot, double* xlon, double* xlat, double* ylon, double* ylat, double* area);
-/* Device-resident variants (new): li, gi/ui/vi, lo, go/uo/vo are DEVICE pointers and so are
- * rlat, rlon, crot, srot (each may be NULL to skip that output; for station-point outputs they are inputs).
- * Scalars, ipopt, the grid definition, ibi, ibo, no and iret stay host memory.  Work is queued on `stream`
- * (a cudaStream_t) and the call returns after that stream has drained. */
+/* Device-resident variants (new): li, gi/ui/vi, lo, go/uo/vo are DEVICE pointers (on the calling
+ * thread's current device) and so are rlat, rlon, crot, srot (each may be NULL to skip that output; for station-point
+ * outputs they are inputs).  Scalars, ipopt, the grid definition, ibi, ibo, no and iret stay host memory.  Work is queued
+ * on `stream` (a cudaStream_t) and the call returns after that stream has drained (ibo is a host output); the
+ * ipgpu_plan_* entry points below queue without waiting. */
 void ipgpu_ipolates_grib2_dev_d(
     void* stream, const int32_t* ip, const int32_t* ipopt, const int32_t* igdtnumi, const int32_t* igdtmpli, const int32_t* igdtleni, const int32_t* igdtnumo, const int32_t* igdtmplo, const int32_t* igdtleno,
     const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const double* gi,
@@ -155,6 +181,29 @@ void ipgpu_ipolatev_grib2_dev_d(
     void* stream, const int32_t* ip, const int32_t* ipopt, const int32_t* igdtnumi, const int32_t* igdtmpli, const int32_t* igdtleni, const int32_t* igdtnumo, const int32_t* igdtmplo, const int32_t* igdtleno,
     const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const double* ui, const double* vi,
     int32_t* no, double* rlat, double* rlon, double* crot, double* srot, int32_t* ibo, ipb_bool* lo, double* uo, double* vo, int32_t* iret);
+/* the same for the GRIB1 interface (kgds arrays of 200 words) */
+void ipgpu_ipolates_grib1_dev_d(
+    void* stream, const int32_t* ip, const int32_t* ipopt, const int32_t* kgdsi, const int32_t* kgdso,
+    const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const double* gi,
+    int32_t* no, double* rlat, double* rlon, int32_t* ibo, ipb_bool* lo, double* go, int32_t* iret);
+void ipgpu_ipolatev_grib1_dev_d(
+    void* stream, const int32_t* ip, const int32_t* ipopt, const int32_t* kgdsi, const int32_t* kgdso,
+    const int32_t* mi, const int32_t* mo, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const double* ui, const double* vi,
+    int32_t* no, double* rlat, double* rlon, double* crot, double* srot, int32_t* ibo, ipb_bool* lo, double* uo, double* vo, int32_t* iret);
+/* Explicit plan handles.  ipgpu_plan_get builds the plan of (grid in, grid out, ip, ipopt) on the
+ * current device or fetches it from that device's cache and returns a handle (NULL on failure: iret as ipolates gives it;
+ * station-point outputs have no cacheable plan).  *vector != 0 asks for the ipolatev plan.  ipgpu_plan_apply queues the
+ * km-field apply stage on `stream` (a cudaStream_t) and RETURNS WITHOUT WAITING: li, gi/ui, vi (NULL for scalars), lo,
+ * go/uo, vo are device pointers; ibi is read from the host before the call returns; ibo_dev (km int32 on the device, may
+ * be NULL) receives ibo when the stream gets there.  ipgpu_plan_geometry copies rlat/rlon(/crot/srot) to host or device
+ * arrays (any may be NULL), queued on `stream`.  Release every handle with ipgpu_plan_release. */
+void* ipgpu_plan_get_d(
+    const int32_t* vector, const int32_t* ip, const int32_t* ipopt, const int32_t* igdtnumi, const int32_t* igdtmpli, const int32_t* igdtleni, const int32_t* igdtnumo, const int32_t* igdtmplo, const int32_t* igdtleno,
+    const int32_t* mi, const int32_t* mo, int32_t* no, int32_t* iret);
+void ipgpu_plan_geometry_d(void* plan, void* stream, double* rlat, double* rlon, double* crot, double* srot, int32_t* iret);
+void ipgpu_plan_apply_d(
+    void* plan, void* stream, const int32_t* km, const int32_t* ibi, const ipb_bool* li, const double* gi, const double* vi,
+    int32_t* ibo_dev, ipb_bool* lo, double* go, double* vo, int32_t* iret);
 
 /* ======================== kind _8  (libip_8: INTEGER(8), REAL(8)) ======================== */
 /* replaces ipolates_grib2, src/ipolates.F90:587-636 */
@@ -207,10 +256,11 @@ void gdswzd_grib1_8(
     const int64_t* kgds, int64_t iopt, int64_t npts, double fill,
     double* xpts, double* ypts, double* rlon, double* rlat, int64_t* nret,
     double* crot, double* srot, double* xlon, double* xlat, double* ylon, double* ylat, double* area);
-/* Device-resident variants (new): li, gi/ui/vi, lo, go/uo/vo are DEVICE pointers and so are
- * rlat, rlon, crot, srot (each may be NULL to skip that output; for station-point outputs they are inputs).
- * Scalars, ipopt, the grid definition, ibi, ibo, no and iret stay host memory.  Work is queued on `stream`
- * (a cudaStream_t) and the call returns after that stream has drained. */
+/* Device-resident variants (new): li, gi/ui/vi, lo, go/uo/vo are DEVICE pointers (on the calling
+ * thread's current device) and so are rlat, rlon, crot, srot (each may be NULL to skip that output; for station-point
+ * outputs they are inputs).  Scalars, ipopt, the grid definition, ibi, ibo, no and iret stay host memory.  Work is queued
+ * on `stream` (a cudaStream_t) and the call returns after that stream has drained (ibo is a host output); the
+ * ipgpu_plan_* entry points below queue without waiting. */
 void ipgpu_ipolates_grib2_dev_8(
     void* stream, const int64_t* ip, const int64_t* ipopt, const int64_t* igdtnumi, const int64_t* igdtmpli, const int64_t* igdtleni, const int64_t* igdtnumo, const int64_t* igdtmplo, const int64_t* igdtleno,
     const int64_t* mi, const int64_t* mo, const int64_t* km, const int64_t* ibi, const ipb_bool* li, const double* gi,
@@ -219,11 +269,36 @@ void ipgpu_ipolatev_grib2_dev_8(
     void* stream, const int64_t* ip, const int64_t* ipopt, const int64_t* igdtnumi, const int64_t* igdtmpli, const int64_t* igdtleni, const int64_t* igdtnumo, const int64_t* igdtmplo, const int64_t* igdtleno,
     const int64_t* mi, const int64_t* mo, const int64_t* km, const int64_t* ibi, const ipb_bool* li, const double* ui, const double* vi,
     int64_t* no, double* rlat, double* rlon, double* crot, double* srot, int64_t* ibo, ipb_bool* lo, double* uo, double* vo, int64_t* iret);
+/* the same for the GRIB1 interface (kgds arrays of 200 words) */
+void ipgpu_ipolates_grib1_dev_8(
+    void* stream, const int64_t* ip, const int64_t* ipopt, const int64_t* kgdsi, const int64_t* kgdso,
+    const int64_t* mi, const int64_t* mo, const int64_t* km, const int64_t* ibi, const ipb_bool* li, const double* gi,
+    int64_t* no, double* rlat, double* rlon, int64_t* ibo, ipb_bool* lo, double* go, int64_t* iret);
+void ipgpu_ipolatev_grib1_dev_8(
+    void* stream, const int64_t* ip, const int64_t* ipopt, const int64_t* kgdsi, const int64_t* kgdso,
+    const int64_t* mi, const int64_t* mo, const int64_t* km, const int64_t* ibi, const ipb_bool* li, const double* ui, const double* vi,
+    int64_t* no, double* rlat, double* rlon, double* crot, double* srot, int64_t* ibo, ipb_bool* lo, double* uo, double* vo, int64_t* iret);
+/* Explicit plan handles.  ipgpu_plan_get builds the plan of (grid in, grid out, ip, ipopt) on the
+ * current device or fetches it from that device's cache and returns a handle (NULL on failure: iret as ipolates gives it;
+ * station-point outputs have no cacheable plan).  *vector != 0 asks for the ipolatev plan.  ipgpu_plan_apply queues the
+ * km-field apply stage on `stream` (a cudaStream_t) and RETURNS WITHOUT WAITING: li, gi/ui, vi (NULL for scalars), lo,
+ * go/uo, vo are device pointers; ibi is read from the host before the call returns; ibo_dev (km int32 on the device, may
+ * be NULL) receives ibo when the stream gets there.  ipgpu_plan_geometry copies rlat/rlon(/crot/srot) to host or device
+ * arrays (any may be NULL), queued on `stream`.  Release every handle with ipgpu_plan_release. */
+void* ipgpu_plan_get_8(
+    const int64_t* vector, const int64_t* ip, const int64_t* ipopt, const int64_t* igdtnumi, const int64_t* igdtmpli, const int64_t* igdtleni, const int64_t* igdtnumo, const int64_t* igdtmplo, const int64_t* igdtleno,
+    const int64_t* mi, const int64_t* mo, int64_t* no, int64_t* iret);
+void ipgpu_plan_geometry_8(void* plan, void* stream, double* rlat, double* rlon, double* crot, double* srot, int64_t* iret);
+void ipgpu_plan_apply_8(
+    void* plan, void* stream, const int64_t* km, const int64_t* ibi, const ipb_bool* li, const double* gi, const double* vi,
+    int32_t* ibo_dev, ipb_bool* lo, double* go, double* vo, int64_t* iret);
 
 /* ======================== library management (new; no reference counterpart) ======================== */
 int ipgpu_device_count(void);                     /* CUDA devices visible to the process */
-int ipgpu_set_device(int device);                 /* cudaSetDevice; call before the first interpolation (one process per GPU) */
-void ipgpu_plan_clear(void);                      /* drop every cached plan and the staging buffers */
+int ipgpu_set_device(int device);                 /* cudaSetDevice for the calling thread; every call works on the device that is current when it enters */
+int ipgpu_set_devices(int n);                     /* host-pointer calls shard their field batch over the first n devices (n <= 1: the current device); returns the count in use */
+void ipgpu_plan_release(void* plan);              /* drops a handle of ipgpu_plan_get_<k> (the plan stays cached) */
+void ipgpu_plan_clear(void);                      /* drop every cached plan and the staging buffers, on every device */
 long long ipgpu_plan_count(void);                 /* plans resident in HBM */
 long long ipgpu_plan_bytes(void);                 /* bytes they hold */
 void ipgpu_set_plan_cache_bytes(long long bytes); /* LRU capacity of the plan cache (default 24 GiB) */
@@ -231,8 +306,10 @@ void ipgpu_set_chunk_bytes(long long bytes);      /* staging size per in-flight 
 long long ipgpu_launch_count(void);               /* kernels launched by this library since load */
 void ipgpu_last_timing(double* plan_ms, double* apply_ms, int* plan_cache_hit); /* CUDA-event times of the last call */
 void ipgpu_last_transfer(long long* h2d_bytes, long long* d2h_bytes); /* field bytes the last host-pointer call moved over PCIe */
-void* ipgpu_host_alloc(long long bytes);          /* pinned host memory (cudaMallocHost) so the host API copies asynchronously */
+void* ipgpu_host_alloc(long long bytes);          /* pinned host memory on the NUMA node of the current device's PCIe link, so the host API copies asynchronously at link rate */
 void ipgpu_host_free(void* p);
+int ipgpu_device_numa_node(void);                 /* NUMA node of the current device's PCIe link, -1 unknown */
+void ipgpu_link_probe(long long bytes, double* h2d_gbs, double* d2h_gbs, double* both_gbs); /* measured host-link ceiling (GB/s) with that allocator */
 const char* ipgpu_version(void);
 /* tile geometry of the point-staged kernels (host-side, for tests): mode 0 = 128 consecutive points, 1 = 32 x 4 patch,
    2 = 16 x 8 patch of an output grid whose rows hold `rowlen` points; the point of (tile, r < 4, lane < 32) or -1 */

@@ -9,12 +9,19 @@
 // <k> = 4 (int32/float), d (int32/double), 8 (int64/double).
 // There is no CPU fallback: every call needs a CUDA device and fails loudly without one.
 #include <cuda_runtime.h>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <cctype>
+#include <cstring>
+#include <mutex>
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <exception>
 #include <vector>
 
 #include "ipb_decode.h"
@@ -23,8 +30,6 @@
 namespace ipb {
 
 std::atomic<long long> g_launches{0};
-bool g_async_alloc = false;
-cudaStream_t g_alloc_stream = nullptr, g_free_stream = nullptr;
 
 #define IPB_CUDA_API(x)                                                                          \
   do {                                                                                           \
@@ -47,25 +52,44 @@ void* DBuf::get(size_t bytes) {
 void DBuf::release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 
 Runtime& rt() { static Runtime r; return r; }
+AllocCtx& alloc_ctx() { static thread_local AllocCtx c; return c; }
 
-void Runtime::ensure_init() {
-  if (init) return;
-  int ndev = 0;
-  cudaError_t e = cudaGetDeviceCount(&ndev);
-  if (e != cudaSuccess || ndev == 0) {
-    fprintf(stderr, "ipb200: no CUDA device available (%s); this library has no CPU path\n", cudaGetErrorString(e));
+int Runtime::current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess) {
+    fprintf(stderr, "ipb200: no CUDA device available (%s); this library has no CPU path\n", cudaGetErrorString(cudaGetLastError()));
     abort();
   }
-  for (int i = 0; i < 2; i++) IPB_CUDA_API(cudaStreamCreateWithFlags(&stream[i], cudaStreamNonBlocking));
-  // keep freed plan memory in the pool (stream-ordered allocations of the plan builder, ipb_plan.cuh: dalloc)
-  int devid = 0;
-  cudaMemPool_t pool;
-  if (cudaGetDevice(&devid) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, devid) == cudaSuccess) {
-    unsigned long long keep = ~0ull;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    g_free_stream = stream[0];
+  return d;
+}
+
+DevState& Runtime::state(int device) {
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev.empty()) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+      fprintf(stderr, "ipb200: no CUDA device available (%s); this library has no CPU path\n", cudaGetErrorString(e));
+      abort();
+    }
+    dev.resize((size_t)ndev);
   }
-  init = true;
+  if (device < 0 || device >= (int)dev.size()) { fprintf(stderr, "ipb200: device %d does not exist\n", device); abort(); }
+  if (!dev[device]) {
+    DeviceGuard guard(device);
+    std::unique_ptr<DevState> d(new DevState());
+    d->device = device;
+    for (int i = 0; i < 2; i++) IPB_CUDA_API(cudaStreamCreateWithFlags(&d->stream[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 3; i++) IPB_CUDA_API(cudaEventCreate(&d->ev[i]));
+    // keep freed plan memory in the pool (stream-ordered allocations of the plan builder, ipb_plan.cuh: dalloc)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    dev[device] = std::move(d);
+  }
+  return *dev[device];
 }
 
 // implemented once per real kind (ipb_kind_f32.cu / ipb_kind_f64.cu)
@@ -86,6 +110,16 @@ extern template void run_gdswzd<float>(GridHost<float>, i64, i64, float, float*,
                                        float*, float*, float*, float*, float*);
 extern template void run_gdswzd<double>(GridHost<double>, i64, i64, double, double*, double*, double*, double*, i64&, double*,
                                         double*, double*, double*, double*, double*, double*);
+
+template <class R> PlanHandle* plan_get(bool, i64, const i64*, const GridHost<R>&, const GridHost<R>&, i64, i64, i64&, i64&);
+template <class R> int plan_geometry(PlanHandle*, void*, R*, R*, R*, R*);
+template <class R> int plan_apply(PlanHandle*, void*, i64, const i64*, const u8*, const R*, const R*, int*, u8*, R*, R*);
+extern template PlanHandle* plan_get<float>(bool, i64, const i64*, const GridHost<float>&, const GridHost<float>&, i64, i64, i64&, i64&);
+extern template PlanHandle* plan_get<double>(bool, i64, const i64*, const GridHost<double>&, const GridHost<double>&, i64, i64, i64&, i64&);
+extern template int plan_geometry<float>(PlanHandle*, void*, float*, float*, float*, float*);
+extern template int plan_geometry<double>(PlanHandle*, void*, double*, double*, double*, double*);
+extern template int plan_apply<float>(PlanHandle*, void*, i64, const i64*, const u8*, const float*, const float*, int*, u8*, float*, float*);
+extern template int plan_apply<double>(PlanHandle*, void*, i64, const i64*, const u8*, const double*, const double*, int*, u8*, double*, double*);
 
 namespace {
 
@@ -124,13 +158,49 @@ void api_interp(bool vec, bool grib2, int dev, void* stream, const I* ip, const 
     if ((iret64 == 0 || budget) && iret64 != 1) for (i64 k = 0; k < km; k++) ibo[k] = (I)ibo64[k];
   } catch (cudaError_t e) {
     *iret = (I)(1000 + (int)e);  // CUDA failures surface as iret >= 1000 (never produced by the reference)
+  } catch (const std::exception& e) {   // host allocation failures etc.: never let a C++ exception cross the C / Fortran frames
+    fprintf(stderr, "ipb200: %s\n", e.what());
+    *iret = (I)1001;
+  } catch (...) {
+    *iret = (I)1001;
   }
+}
+
+// shared by the handle entry points
+template <class R, class I>
+PlanHandle* api_plan_get(bool vec, const I* ip, const I* ipopt, const I* numi, const I* dsci, const I* leni, const I* numo, const I* dsco,
+                         const I* leno, const I* mi, const I* mo, I* no, I* iret) {
+  try {
+    auto ti = widen(dsci, *leni), to = widen(dsco, *leno);
+    GridHost<R> gin = decode_grib2<R>(*numi, ti.data(), *leni), gout = decode_grib2<R>(*numo, to.data(), *leno);
+    auto opt = widen(ipopt, 20);
+    i64 no64 = 0, iret64 = 0;
+    PlanHandle* h = plan_get<R>(vec, *ip, opt.data(), gin, gout, *mi, *mo, no64, iret64);
+    *no = (I)no64; *iret = (I)iret64;
+    return h;
+  } catch (cudaError_t e) { *iret = (I)(1000 + (int)e); } catch (...) { *iret = (I)1001; }
+  return nullptr;
+}
+template <class R, class I>
+void api_plan_apply(PlanHandle* h, void* stream, i64 km, const I* ibi, const u8* li, const R* gi, const R* vi, int32_t* d_ibo, u8* lo, R* go,
+                    R* vo, I* iret) {
+  try {
+    auto ib = widen(ibi, km);
+    const int rc = plan_apply<R>(h, stream, km, ib.data(), li, gi, vi, d_ibo, lo, go, vo);
+    *iret = rc ? (I)1 : (I)(h ? h->iret : 1);
+  } catch (cudaError_t e) { *iret = (I)(1000 + (int)e); } catch (...) { *iret = (I)1001; }
 }
 
 }  // namespace
 }  // namespace ipb
 
 using namespace ipb;
+
+namespace {
+struct HostMap { void* p; size_t len; };
+std::mutex g_host_mu;
+std::vector<HostMap> g_host_maps;
+}  // namespace
 
 #define IPB_KIND(SFX, R, I)                                                                                              \
   extern "C" {                                                                                                           \
@@ -202,6 +272,32 @@ using namespace ipb;
     api_interp<R, I>(true, true, 1, stream, ip, ipopt, numi, tmpli, leni, numo, tmplo, leno, mi, mo, *km, ibi, li, ui,   \
                      vi, no, rlat, rlon, crot, srot, ibo, lo, uo, vo, iret);                                             \
   }                                                                                                                      \
+  void ipgpu_ipolates_grib1_dev_##SFX(void* stream, const I* ip, const I* ipopt, const I* kgdsi, const I* kgdso,         \
+                                      const I* mi, const I* mo, const I* km, const I* ibi, const u8* li, const R* gi,    \
+                                      I* no, R* rlat, R* rlon, I* ibo, u8* lo, R* go, I* iret) {                          \
+    api_interp<R, I>(false, false, 1, stream, ip, ipopt, nullptr, kgdsi, nullptr, nullptr, kgdso, nullptr, mi, mo, *km,  \
+                     ibi, li, gi, nullptr, no, rlat, rlon, nullptr, nullptr, ibo, lo, go, nullptr, iret);                \
+  }                                                                                                                      \
+  void ipgpu_ipolatev_grib1_dev_##SFX(void* stream, const I* ip, const I* ipopt, const I* kgdsi, const I* kgdso,         \
+                                      const I* mi, const I* mo, const I* km, const I* ibi, const u8* li, const R* ui,    \
+                                      const R* vi, I* no, R* rlat, R* rlon, R* crot, R* srot, I* ibo, u8* lo, R* uo,     \
+                                      R* vo, I* iret) {                                                                  \
+    api_interp<R, I>(true, false, 1, stream, ip, ipopt, nullptr, kgdsi, nullptr, nullptr, kgdso, nullptr, mi, mo, *km,   \
+                     ibi, li, ui, vi, no, rlat, rlon, crot, srot, ibo, lo, uo, vo, iret);                                \
+  }                                                                                                                      \
+  /* explicit plan handles: build / fetch once, then queue applies without draining the stream */                       \
+  void* ipgpu_plan_get_##SFX(const I* vector, const I* ip, const I* ipopt, const I* numi, const I* tmpli, const I* leni, \
+                             const I* numo, const I* tmplo, const I* leno, const I* mi, const I* mo, I* no, I* iret) {   \
+    return api_plan_get<R, I>(*vector != 0, ip, ipopt, numi, tmpli, leni, numo, tmplo, leno, mi, mo, no, iret);          \
+  }                                                                                                                      \
+  void ipgpu_plan_geometry_##SFX(void* plan, void* stream, R* rlat, R* rlon, R* crot, R* srot, I* iret) {                \
+    try { *iret = (I)plan_geometry<R>((PlanHandle*)plan, stream, rlat, rlon, crot, srot); }                             \
+    catch (cudaError_t e) { *iret = (I)(1000 + (int)e); } catch (...) { *iret = (I)1001; }                               \
+  }                                                                                                                      \
+  void ipgpu_plan_apply_##SFX(void* plan, void* stream, const I* km, const I* ibi, const u8* li, const R* gi,            \
+                              const R* vi, int32_t* ibo_dev, u8* lo, R* go, R* vo, I* iret) {                            \
+    api_plan_apply<R, I>((PlanHandle*)plan, stream, *km, ibi, li, gi, vi, ibo_dev, lo, go, vo, iret);                    \
+  }                                                                                                                      \
   void gdswzd_##SFX(I num, const I* tmpl, I len, I iopt, I npts, R fill, R* xpts, R* ypts, R* rlon, R* rlat, I* nret,    \
                     R* crot, R* srot, R* xlon, R* xlat, R* ylon, R* ylat, R* area) {                                     \
     try {                                                                                                                \
@@ -210,7 +306,7 @@ using namespace ipb;
       run_gdswzd<R>(decode_grib2<R>(num, t.data(), len), iopt, npts, fill, xpts, ypts, rlon, rlat, nr, crot, srot, xlon, \
                     xlat, ylon, ylat, area);                                                                             \
       *nret = (I)nr;                                                                                                     \
-    } catch (cudaError_t) { *nret = 0; }                                                                                 \
+    } catch (...) { *nret = 0; }                                                                                         \
   }                                                                                                                      \
   void gdswzd_grib1_##SFX(const I* kgds, I iopt, I npts, R fill, R* xpts, R* ypts, R* rlon, R* rlat, I* nret, R* crot,   \
                           R* srot, R* xlon, R* xlat, R* ylon, R* ylat, R* area) {                                        \
@@ -220,7 +316,7 @@ using namespace ipb;
       run_gdswzd<R>(decode_grib1<R>(t.data()), iopt, npts, fill, xpts, ypts, rlon, rlat, nr, crot, srot, xlon, xlat,     \
                     ylon, ylat, area);                                                                                   \
       *nret = (I)nr;                                                                                                     \
-    } catch (cudaError_t) { *nret = 0; }                                                                                 \
+    } catch (...) { *nret = 0; }                                                                                         \
   }                                                                                                                      \
   }
 
@@ -232,14 +328,41 @@ extern "C" {
 // library management (new; no reference counterpart)
 int ipgpu_device_count() { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
 int ipgpu_set_device(int d) { return (int)cudaSetDevice(d); }
-void ipgpu_plan_clear() {
+// Host-pointer calls shard their field batch over the first n devices (one host thread, one PCIe link and one plan copy
+// each); n <= 1 restores the default (the calling thread's current device).  Returns the number of devices in use.
+int ipgpu_set_devices(int n) {
+  int have = ipgpu_device_count();
   Runtime& RT = rt();
   std::lock_guard<std::mutex> lock(RT.mu);
-  RT.cache.clear();
-  for (int i = 0; i < 2; i++) { Work& w = RT.work[i]; w.gi.release(); w.vi.release(); w.li.release(); w.go.release(); w.vo.release(); w.lo.release(); w.ints.release(); }
+  RT.shard.clear();
+  if (n > have) n = have;
+  if (n > 1) for (int d = 0; d < n; d++) RT.shard.push_back(d);
+  return n > 1 ? n : 1;
 }
-long long ipgpu_plan_count() { Runtime& RT = rt(); std::lock_guard<std::mutex> lock(RT.mu); return (long long)RT.cache.size(); }
-long long ipgpu_plan_bytes() { Runtime& RT = rt(); std::lock_guard<std::mutex> lock(RT.mu); size_t t = 0; for (auto& e : RT.cache) t += e.bytes; return (long long)t; }
+void ipgpu_plan_release(void* plan) { delete (PlanHandle*)plan; }
+void ipgpu_plan_clear() {
+  Runtime& RT = rt();
+  std::vector<DevState*> all;
+  { std::lock_guard<std::mutex> lock(RT.mu); for (auto& d : RT.dev) if (d) all.push_back(d.get()); }
+  for (DevState* d : all) {
+    std::lock_guard<std::mutex> lock(d->mu);
+    DeviceGuard guard(d->device);
+    d->cache.clear();
+    for (int i = 0; i < 2; i++) { Work& w = d->work[i]; w.gi.release(); w.vi.release(); w.li.release(); w.go.release(); w.vo.release(); w.lo.release(); w.ints.release(); }
+  }
+}
+long long ipgpu_plan_count() {
+  Runtime& RT = rt(); long long n = 0;
+  std::lock_guard<std::mutex> lock(RT.mu);
+  for (auto& d : RT.dev) if (d) { std::lock_guard<std::mutex> l2(d->mu); n += (long long)d->cache.size(); }
+  return n;
+}
+long long ipgpu_plan_bytes() {
+  Runtime& RT = rt(); size_t t = 0;
+  std::lock_guard<std::mutex> lock(RT.mu);
+  for (auto& d : RT.dev) if (d) { std::lock_guard<std::mutex> l2(d->mu); for (auto& e : d->cache) t += e.bytes; }
+  return (long long)t;
+}
 void ipgpu_set_plan_cache_bytes(long long b) { Runtime& RT = rt(); std::lock_guard<std::mutex> lock(RT.mu); RT.cache_cap = (size_t)b; }
 void ipgpu_set_chunk_bytes(long long b) { Runtime& RT = rt(); std::lock_guard<std::mutex> lock(RT.mu); RT.chunk_bytes = (size_t)std::max<long long>(b, 1 << 20); }
 long long ipgpu_launch_count() { return g_launches.load(); }
@@ -255,7 +378,98 @@ void ipgpu_last_transfer(long long* h2d_bytes, long long* d2h_bytes) {
   if (h2d_bytes) *h2d_bytes = RT.last_h2d;
   if (d2h_bytes) *d2h_bytes = RT.last_d2h;
 }
-void* ipgpu_host_alloc(long long bytes) { void* p = nullptr; if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
-void ipgpu_host_free(void* p) { if (p) cudaFreeHost(p); }
-const char* ipgpu_version() { return "ipb200 0.1 (sm_100a)"; }
+// Pinned host memory for the host-pointer API.  The pages are placed on the NUMA node the current device's PCIe link
+// hangs off (mbind + first touch, then cudaHostRegister): a buffer on the far socket halves the link rate.  Falls back to
+// cudaMallocHost when the node is unknown or the policy call is not permitted.
+void* ipgpu_host_alloc(long long bytes) {
+  if (bytes <= 0) return nullptr;
+  int dev = 0, node = -1;
+  char bus[64] = {0};
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetPCIBusId(bus, sizeof(bus), dev) == cudaSuccess) {
+    for (char* c = bus; *c; c++) *c = (char)tolower(*c);
+    char path[160];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    if (FILE* f = fopen(path, "r")) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+  }
+  static const bool numa_off = getenv("IPB_NO_NUMA") != nullptr;
+  if (node >= 0 && node < 1024 && !numa_off) {
+    const size_t len = ((size_t)bytes + 4095) & ~(size_t)4095;
+    void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p != MAP_FAILED) {
+      unsigned long mask[16] = {0};
+      mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+      (void)syscall(SYS_mbind, p, len, 2 /* MPOL_BIND */, mask, (unsigned long)(8 * sizeof(mask)), 0u);   // best effort
+      memset(p, 0, len);                                                                                   // first touch places the pages
+      if (cudaHostRegister(p, len, cudaHostRegisterPortable) == cudaSuccess) {
+        std::lock_guard<std::mutex> lock(g_host_mu);
+        g_host_maps.push_back({p, len});
+        return p;
+      }
+      cudaGetLastError();
+      munmap(p, len);
+    }
+  }
+  void* p = nullptr;
+  if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void ipgpu_host_free(void* p) {
+  if (!p) return;
+  {
+    std::lock_guard<std::mutex> lock(g_host_mu);
+    for (size_t i = 0; i < g_host_maps.size(); i++)
+      if (g_host_maps[i].p == p) {
+        cudaHostUnregister(p);
+        munmap(p, g_host_maps[i].len);
+        g_host_maps.erase(g_host_maps.begin() + (long)i);
+        return;
+      }
+  }
+  cudaFreeHost(p);
+}
+// NUMA node of the current device's PCIe link (-1 unknown)
+int ipgpu_device_numa_node() {
+  int dev = 0, node = -1;
+  char bus[64] = {0};
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetPCIBusId(bus, sizeof(bus), dev) == cudaSuccess) {
+    for (char* c = bus; *c; c++) *c = (char)tolower(*c);
+    char path[160];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    if (FILE* f = fopen(path, "r")) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+  }
+  return node;
+}
+// Measured ceiling of the current device's host link with this library's own pinned allocator: GB/s of one large
+// host->device and one device->host copy, and of both directions at once (what a streamed call can reach at best).
+void ipgpu_link_probe(long long bytes, double* h2d_gbs, double* d2h_gbs, double* both_gbs) {
+  if (h2d_gbs) *h2d_gbs = 0; if (d2h_gbs) *d2h_gbs = 0; if (both_gbs) *both_gbs = 0;
+  if (bytes < (1 << 20)) bytes = 1 << 20;
+  void *h0 = ipgpu_host_alloc(bytes), *h1 = ipgpu_host_alloc(bytes), *d0 = nullptr, *d1 = nullptr;
+  cudaStream_t s0 = nullptr, s1 = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h0 && h1 && cudaMalloc(&d0, (size_t)bytes) == cudaSuccess && cudaMalloc(&d1, (size_t)bytes) == cudaSuccess &&
+      cudaStreamCreate(&s0) == cudaSuccess && cudaStreamCreate(&s1) == cudaSuccess && cudaEventCreate(&e0) == cudaSuccess &&
+      cudaEventCreate(&e1) == cudaSuccess) {
+    float ms = 0;
+    for (int rep = 0; rep < 2; rep++) {   // second repetition is the measurement
+      cudaEventRecord(e0, s0); cudaMemcpyAsync(d0, h0, (size_t)bytes, cudaMemcpyHostToDevice, s0); cudaEventRecord(e1, s0); cudaEventSynchronize(e1);
+      cudaEventElapsedTime(&ms, e0, e1); if (h2d_gbs) *h2d_gbs = bytes / (ms * 1e6);
+      cudaEventRecord(e0, s0); cudaMemcpyAsync(h1, d1, (size_t)bytes, cudaMemcpyDeviceToHost, s0); cudaEventRecord(e1, s0); cudaEventSynchronize(e1);
+      cudaEventElapsedTime(&ms, e0, e1); if (d2h_gbs) *d2h_gbs = bytes / (ms * 1e6);
+      cudaStreamSynchronize(s1);
+      cudaEventRecord(e0, s0);
+      cudaMemcpyAsync(d0, h0, (size_t)bytes, cudaMemcpyHostToDevice, s0);
+      cudaMemcpyAsync(h1, d1, (size_t)bytes, cudaMemcpyDeviceToHost, s1);
+      cudaStreamSynchronize(s1);
+      cudaEventRecord(e1, s0); cudaEventSynchronize(e1);
+      cudaEventElapsedTime(&ms, e0, e1); if (both_gbs) *both_gbs = 2.0 * bytes / (ms * 1e6);
+    }
+  }
+  cudaGetLastError();
+  if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1);
+  if (s0) cudaStreamDestroy(s0); if (s1) cudaStreamDestroy(s1);
+  if (d0) cudaFree(d0); if (d1) cudaFree(d1);
+  ipgpu_host_free(h0); ipgpu_host_free(h1);
+}
+const char* ipgpu_version() { return "ipb200 0.2 (sm_100a)"; }
 }

@@ -101,13 +101,16 @@ k_apply_stencil(FieldArgs<R> a, GridP<R> gin, int kpb, const int* __restrict__ n
   for (int k = k0; k < k1; k++) {
     const R* __restrict__ g = a.gi + (size_t)k * a.mi;
     const R* __restrict__ gv = VEC ? a.vi + (size_t)k * a.mi : nullptr;
-    const bool masked = a.ibi[k] != 0;
+    // a.li is null when no field of the call carries a bitmap: the ibi loads then stay off the critical path
+    const bool masked = a.li != nullptr && a.ibi[k] != 0;
     const u8* __restrict__ l = a.li ? a.li + (size_t)k * a.mi : nullptr;
     const size_t oa = (size_t)k * a.mo + n;
     if (complete && !masked) {   // complete also means the weight sum passes the threshold
       // KU fields per iteration with all their gathers issued first: this loop is bound by gather latency
-      constexpr int KU = (NT == 2) ? 2 : 1;
-      const int ku = (KU == 2 && k + 1 < k1 && a.ibi[k + 1] == 0) ? 2 : 1;
+      // (ncu, vector bilinear S -> P: 43 % of the warps' time waiting on the gathers with two pairs in flight)
+      constexpr int KU = (NT == 2) ? 4 : 1;
+      int ku = 1;
+      if (KU > 1) while (ku < KU && k + ku < k1 && (a.li == nullptr || a.ibi[k + ku] == 0)) ku++;
       R tv[KU][T2], tu[KU][VEC ? T2 : 1];
 #pragma unroll
       for (int q = 0; q < KU; q++) {

@@ -7,6 +7,8 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <stdexcept>
+#include <thread>
 
 #include "ipb_apply.cuh"
 #include "ipb_fast.cuh"
@@ -29,30 +31,26 @@ std::vector<i64> plan_key(int method, bool vec, const i64* ipopt, const GridHost
   return k;
 }
 
-template <class R> std::shared_ptr<Plan<R>> cache_find(const std::vector<i64>& key) {
-  Runtime& RT = rt();
-  for (auto& e : RT.cache)
-    if (e.kind == (int)sizeof(R) && e.key == key) { e.stamp = ++RT.stamp; return std::static_pointer_cast<Plan<R>>(e.plan); }
+template <class R> std::shared_ptr<Plan<R>> cache_find(DevState& DS, const std::vector<i64>& key) {
+  for (auto& e : DS.cache)
+    if (e.kind == (int)sizeof(R) && e.key == key) { e.stamp = ++DS.stamp; return std::static_pointer_cast<Plan<R>>(e.plan); }
   return nullptr;
 }
-template <class R> void cache_put(const std::vector<i64>& key, std::shared_ptr<Plan<R>> p) {
-  Runtime& RT = rt();
+template <class R> void cache_put(DevState& DS, const std::vector<i64>& key, std::shared_ptr<Plan<R>> p) {
+  const size_t cap = rt().cache_cap;
   size_t tot = p->bytes;
-  for (auto& e : RT.cache) tot += e.bytes;
-  while (tot > RT.cache_cap && !RT.cache.empty()) {
-    auto it = std::min_element(RT.cache.begin(), RT.cache.end(), [](const CacheEntry& a, const CacheEntry& b) { return a.stamp < b.stamp; });
+  for (auto& e : DS.cache) tot += e.bytes;
+  while (tot > cap && !DS.cache.empty()) {
+    auto it = std::min_element(DS.cache.begin(), DS.cache.end(), [](const CacheEntry& a, const CacheEntry& b) { return a.stamp < b.stamp; });
     tot -= it->bytes;
-    RT.cache.erase(it);
+    DS.cache.erase(it);
   }
-  RT.cache.push_back({key, std::static_pointer_cast<void>(p), (int)sizeof(R), p->bytes, ++RT.stamp});
+  DS.cache.push_back({key, std::static_pointer_cast<void>(p), (int)sizeof(R), p->bytes, ++DS.stamp});
 }
-
-
-// While one of these is alive (always under the runtime mutex) dalloc/dfree are stream-ordered on `s`.
-struct AsyncAlloc {
-  AsyncAlloc(cudaStream_t s) { g_alloc_stream = s; g_async_alloc = true; }
-  ~AsyncAlloc() { g_async_alloc = false; }
-};
+// the cache entry's size follows a plan that grows after it was cached (tables added on first need)
+template <class R> void cache_resize(DevState& DS, const std::shared_ptr<Plan<R>>& p) {
+  for (auto& e : DS.cache) if (e.plan.get() == (void*)p.get()) e.bytes = p->bytes;
+}
 
 // ---- one launch of the apply stage over kc fields already resident on the device ------------------
 template <class R>
@@ -129,30 +127,12 @@ void launch_post(const Plan<R>& P, bool vec, const FieldArgs<R>& a, int* d_ibo, 
   }
 }
 
-// ---- the driver shared by ipolates / ipolatev ------------------------------------------------------
-// dev = 1: li/gi/vi/lo/go/vo are device pointers and everything runs on `user_stream`.
-template <class R>
-void run(bool vec, int dev, void* user_stream, i64 ip, const i64* ipopt, const GridHost<R>& gin, const GridHost<R>& gout, i64 mi,
-         i64 mo, i64 km, const i64* ibi, const u8* li, const R* gi, const R* vi, i64& no, R* rlat, R* rlon, R* crot, R* srot,
-         i64* ibo, u8* lo, R* go, R* vo, i64& iret) {
-  Runtime& RT = rt();
-  std::lock_guard<std::mutex> lock(RT.mu);
-  RT.ensure_init();
-  iret = 0;
-  if (!(ip == 0 || ip == 1 || ip == 2 || ip == 3 || ip == 6)) {
-    // ip=4 (spectral) is outside this library's scope; other values make the reference error-stop.
-    fprintf(stderr, "ipb200: interpolation method ip=%lld is not supported (0,1,2,3,6 are)\n", (long long)ip);
-    iret = 1; return;
-  }
-  if (!gin.ok || !gout.ok) { fprintf(stderr, "ipb200: unrecognised grid definition\n"); iret = 1; return; }
-  if (mi >= ((i64)1 << 31) || mo >= ((i64)1 << 31) || km < 0) { iret = 1; return; }
-  const int method = (int)ip;
-  const bool budget = method == M_BUDGET || method == M_NBUDGET;
-  const bool station = gout.p.type == P_STATION;
-  cudaStream_t st0 = dev ? (cudaStream_t)user_stream : RT.stream[0];
-
-  // option decode of the stencil methods (bilinear_interp_mod.F90:110-115, bicubic :117-122, neighbor :135)
-  i64 mp = 50, mcon = 0, mspiral = 0;
+// ---- options and plans -----------------------------------------------------------------------------
+// option decode of the stencil methods (bilinear_interp_mod.F90:110-115, bicubic :117-122, neighbor :135); the budget
+// family's threshold comes from its plan (decode_budget_opt).  Returns iret (0 or 32).
+template <class R> struct ApplyOpts { R pmp = 0; int mcon = 0, mspiral = 0; };
+template <class R> i64 decode_opts(int method, const i64* ipopt, ApplyOpts<R>& o) {
+  i64 mp = 50, mcon = 0, mspiral = 0, iret = 0;
   if (method == M_BILINEAR) { mp = ipopt[0]; mspiral = std::max<i64>(ipopt[1], 0); }
   else if (method == M_BICUBIC) { mcon = ipopt[0]; mp = ipopt[1]; }
   else if (method == M_NEIGHBOR) { mspiral = std::max<i64>(ipopt[0], 1); }
@@ -161,37 +141,69 @@ void run(bool vec, int dev, void* user_stream, i64 ip, const i64* ipopt, const G
     if (mp == -1 || mp == 0) mp = 50;
     if (mp < 0 || mp > 100) iret = 32;
   }
-  R pmp = (R)mp * IPB_RC(0.01);
-  if (!budget && iret != 0) { if (!station) no = 0; return; }
+  o.pmp = (R)mp * IPB_RC(0.01); o.mcon = (int)mcon; o.mspiral = (int)mspiral;
+  return iret;
+}
 
-  // plan: cached per grid pair (never for station points, whose coordinates are call arguments)
+// The plan of a call: fetched from the device's cache or built on `st` (never cached for station points, whose
+// coordinates are call arguments).  Caller holds DS.mu and has DS.device current.
+template <class R>
+std::shared_ptr<Plan<R>> obtain_plan(DevState& DS, int method, bool vec, const i64* ipopt, const GridHost<R>& gin, const GridHost<R>& gout,
+                                     i64 mi, i64 mo, i64 no_in, const R* rlat, const R* rlon, const R* crot, const R* srot, bool any_mask,
+                                     cudaStream_t st, int& hit) {
+  const bool station = gout.p.type == P_STATION;
   std::shared_ptr<Plan<R>> P;
   std::vector<i64> key = plan_key<R>(method, vec, ipopt, gin, gout, mi, mo);
-  cudaEvent_t t0, t1, t2;
-  cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventCreate(&t2);
-  cudaEventRecord(t0, st0);
-  RT.last_plan_hit = 0; RT.last_h2d = 0; RT.last_d2h = 0;
-  if (!station) { P = cache_find<R>(key); if (P) RT.last_plan_hit = 1; }
+  hit = 0;
+  if (!station) { P = cache_find<R>(DS, key); if (P) hit = 1; }
   if (!P) {
-    AsyncAlloc scope(st0);   // plan arrays come from the memory pool, ordered on the stream that builds and first uses them
-    P.reset(build_plan<R>(method, vec, ipopt, gin, gout, mi, mo, no, rlat, rlon, crot, srot, st0));
-    if (P->iret == 0 && !station) { build_tile_tables<R>(*P, st0); P->bytes += P->tiles.bytes; build_box_tables<R>(*P, st0); }
-    if (P->iret == 0) build_budget_collapse<R>(*P, st0);
-    if (P->iret == 0 && !station && method != M_BILINEAR) { build_gtiles<R>(*P, st0); P->bytes += P->gt.bytes; }
-    if (!station) cache_put<R>(key, P);
+    AsyncAlloc scope(st);   // plan arrays come from the memory pool, ordered on the stream that builds and first uses them
+    P.reset(build_plan<R>(method, vec, ipopt, gin, gout, mi, mo, no_in, rlat, rlon, crot, srot, st));
+    P->free_stream = DS.stream[0];
+    if (P->iret == 0 && !station) { build_tile_tables<R>(*P, st); P->bytes += P->tiles.bytes; build_box_tables<R>(*P, st); }
+    if (P->iret == 0) build_budget_collapse<R>(*P, st);
+    if (P->iret == 0 && !station && method != M_BILINEAR) { build_gtiles<R>(*P, st); P->bytes += P->gt.bytes; }
+    if (!station) cache_put<R>(DS, key, P);
   }
   // bilinear calls that carry a bitmap use the point-staged kernel; its tables are added to the plan on first need
-  if (P->iret == 0 && !station && method == M_BILINEAR && !vec && !P->gt.ok && !P->gt_tried && km > 0) {
-    bool anym = false;
-    for (i64 k = 0; k < km; k++) anym = anym || ibi[k] != 0;
-    if (anym) {
-      AsyncAlloc scope(st0);
-      P->gt_tried = true;
-      build_gtiles<R>(*P, st0);
-      P->bytes += P->gt.bytes;
-    }
+  if (P->iret == 0 && !station && method == M_BILINEAR && !vec && !P->gt.ok && !P->gt_tried && any_mask) {
+    AsyncAlloc scope(st);
+    P->gt_tried = true;
+    build_gtiles<R>(*P, st);
+    P->bytes += P->gt.bytes;
+    cache_resize<R>(DS, P);
   }
-  cudaEventRecord(t1, st0);
+  return P;
+}
+
+// ---- the driver shared by ipolates / ipolatev, on one device ---------------------------------------
+// dev = 1: li/gi/vi/lo/go/vo are device pointers and everything runs on `user_stream`.
+template <class R>
+void run_on(int device, bool stats, bool vec, int dev, void* user_stream, i64 ip, const i64* ipopt, const GridHost<R>& gin,
+            const GridHost<R>& gout, i64 mi, i64 mo, i64 km, const i64* ibi, const u8* li, const R* gi, const R* vi, i64& no, R* rlat,
+            R* rlon, R* crot, R* srot, i64* ibo, u8* lo, R* go, R* vo, i64& iret) {
+  Runtime& RT = rt();
+  DeviceGuard guard(device);
+  DevState& DS = RT.state(device);
+  std::lock_guard<std::mutex> lock(DS.mu);
+  iret = 0;
+  const int method = (int)ip;
+  const bool budget = method == M_BUDGET || method == M_NBUDGET;
+  const bool station = gout.p.type == P_STATION;
+  cudaStream_t st0 = dev ? (cudaStream_t)user_stream : DS.stream[0];
+  ApplyOpts<R> o;
+  iret = decode_opts<R>(method, ipopt, o);
+  R pmp = o.pmp;
+  const i64 mcon = o.mcon, mspiral = o.mspiral;
+  if (!budget && iret != 0) { if (!station) no = 0; return; }
+
+  bool any_mask = false;
+  for (i64 k = 0; k < km; k++) if (ibi[k] != 0) any_mask = true;
+  cudaEventRecord(DS.ev[0], st0);
+  int hit = 0;
+  std::shared_ptr<Plan<R>> P = obtain_plan<R>(DS, method, vec, ipopt, gin, gout, mi, mo, no, rlat, rlon, crot, srot, any_mask && km > 0, st0, hit);
+  long long h2d = 0, d2h = 0;
+  cudaEventRecord(DS.ev[1], st0);
   const int NO = P->no;
   // lat/lon (and rotations) are outputs for real grids; for stations the budget-family vector
   // routines overwrite crot/srot (see k_out_geo)
@@ -218,15 +230,12 @@ void run(bool vec, int dev, void* user_stream, i64 ip, const i64* ipopt, const G
     copy_geo(st0);
     IPB_CUDA(cudaStreamSynchronize(st0));
     if (!station) no = 0;
-    cudaEventDestroy(t0); cudaEventDestroy(t1); cudaEventDestroy(t2);
     return;
   } else {
     no = station ? mo : NO;
   }
   copy_geo(st0);
 
-  bool any_mask = false;
-  for (i64 k = 0; k < km; k++) if (ibi[k] != 0) any_mask = true;
   std::vector<int> ibi32(std::max<i64>(km, 1));
   for (i64 k = 0; k < km; k++) ibi32[k] = ibi[k] != 0 ? (int)ibi[k] : 0;
   std::vector<int> ibo32(std::max<i64>(km, 1), 0);
@@ -234,7 +243,7 @@ void run(bool vec, int dev, void* user_stream, i64 ip, const i64* ipopt, const G
   if (NO > 0 && km > 0) {
     if (dev) {
       // whole batch in one pass on the caller's stream
-      int* d_int = (int*)RT.work[0].ints.get((size_t)km * 3 * sizeof(int));
+      int* d_int = (int*)DS.work[0].ints.get((size_t)km * 3 * sizeof(int));
       IPB_CUDA(cudaMemcpyAsync(d_int, ibi32.data(), km * sizeof(int), cudaMemcpyHostToDevice, st0));
       IPB_CUDA(cudaMemsetAsync(d_int + km, 0, km * sizeof(int), st0));
       FieldArgs<R> a{NO, (int)mi, (int)mo, (int)km, gi, vi, any_mask ? li : nullptr, d_int, go, vo, lo, d_int + km, pmp, (int)mcon, (int)mspiral};
@@ -256,8 +265,8 @@ void run(bool vec, int dev, void* user_stream, i64 ip, const i64* ipopt, const G
       int ci = 0;
       for (i64 k0 = 0; k0 < km; k0 += kc, ci ^= 1) {
         const i64 kn = std::min(kc, km - k0);
-        cudaStream_t s = RT.stream[ci];
-        Work& w = RT.work[ci];
+        cudaStream_t s = DS.stream[ci];
+        Work& w = DS.work[ci];
         IPB_CUDA(cudaStreamSynchronize(s));  // buffers of this slot are free again
         R* d_gi = (R*)w.gi.get((size_t)kn * mi * sizeof(R));
         R* d_vi = vec ? (R*)w.vi.get((size_t)kn * mi * sizeof(R)) : nullptr;
@@ -267,7 +276,7 @@ void run(bool vec, int dev, void* user_stream, i64 ip, const i64* ipopt, const G
         u8* d_lo = (u8*)w.lo.get((size_t)kn * mo);
         int* d_int = (int*)w.ints.get((size_t)kn * 3 * sizeof(int));
         // only the window of the input field the plan refers to crosses PCIe (the spiral searches can leave it)
-        RT.last_h2d += (long long)win_n * kn * (sizeof(R) * (vec ? 2 : 1) + (any_mask ? 1 : 0));
+        h2d += (long long)win_n * kn * (sizeof(R) * (vec ? 2 : 1) + (any_mask ? 1 : 0));
         if (win_lo == 0 && win_n == (size_t)mi) {
           IPB_CUDA(cudaMemcpyAsync(d_gi, gi + (size_t)k0 * mi, (size_t)kn * mi * sizeof(R), cudaMemcpyHostToDevice, s));
           if (vec) IPB_CUDA(cudaMemcpyAsync(d_vi, vi + (size_t)k0 * mi, (size_t)kn * mi * sizeof(R), cudaMemcpyHostToDevice, s));
@@ -283,7 +292,7 @@ void run(bool vec, int dev, void* user_stream, i64 ip, const i64* ipopt, const G
         launch_apply<R>(*P, vec, a, s);
         launch_post<R>(*P, vec, a, d_int + 2 * kn, s);
         // only the first NO points of each field are defined (the reference leaves the rest untouched)
-        RT.last_d2h += (long long)NO * kn * (sizeof(R) * (vec ? 2 : 1) + 1);
+        d2h += (long long)NO * kn * (sizeof(R) * (vec ? 2 : 1) + 1);
         if (NO == mo) {
           IPB_CUDA(cudaMemcpyAsync(go + (size_t)k0 * mo, d_go, (size_t)kn * mo * sizeof(R), cudaMemcpyDeviceToHost, s));
           if (vec) IPB_CUDA(cudaMemcpyAsync(vo + (size_t)k0 * mo, d_vo, (size_t)kn * mo * sizeof(R), cudaMemcpyDeviceToHost, s));
@@ -295,20 +304,162 @@ void run(bool vec, int dev, void* user_stream, i64 ip, const i64* ipopt, const G
         }
         IPB_CUDA(cudaMemcpyAsync(ibo32.data() + k0, d_int + 2 * kn, kn * sizeof(int), cudaMemcpyDeviceToHost, s));
       }
-      IPB_CUDA(cudaStreamSynchronize(RT.stream[0]));
-      IPB_CUDA(cudaStreamSynchronize(RT.stream[1]));
+      IPB_CUDA(cudaStreamSynchronize(DS.stream[0]));
+      IPB_CUDA(cudaStreamSynchronize(DS.stream[1]));
     }
     for (i64 k = 0; k < km; k++) ibo[k] = ibo32[k];
   } else {
     IPB_CUDA(cudaStreamSynchronize(st0));
     for (i64 k = 0; k < km; k++) ibo[k] = ibi[k];
   }
-  cudaEventRecord(t2, st0);
-  cudaEventSynchronize(t2);
-  float ms = 0;
-  cudaEventElapsedTime(&ms, t0, t1); RT.last_plan_ms = ms;
-  cudaEventElapsedTime(&ms, t1, t2); RT.last_apply_ms = ms;
-  cudaEventDestroy(t0); cudaEventDestroy(t1); cudaEventDestroy(t2);
+  cudaEventRecord(DS.ev[2], st0);
+  cudaEventSynchronize(DS.ev[2]);
+  if (stats) {
+    std::lock_guard<std::mutex> g(RT.mu);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, DS.ev[0], DS.ev[1]); RT.last_plan_ms = ms;
+    cudaEventElapsedTime(&ms, DS.ev[1], DS.ev[2]); RT.last_apply_ms = ms;
+    RT.last_plan_hit = hit;
+  }
+  {
+    std::lock_guard<std::mutex> g(RT.mu);
+    RT.last_h2d += h2d; RT.last_d2h += d2h;
+  }
+}
+
+// ---- the entry: argument checks, then one device or — host pointers after ipgpu_set_devices(n) — the field batch
+// sharded over n devices, one host thread and one PCIe link each (fields are independent given the
+// plan; every device builds or fetches its own copy of the plan, bit-identical by construction) -------------------------
+template <class R>
+void run(bool vec, int dev, void* user_stream, i64 ip, const i64* ipopt, const GridHost<R>& gin, const GridHost<R>& gout, i64 mi,
+         i64 mo, i64 km, const i64* ibi, const u8* li, const R* gi, const R* vi, i64& no, R* rlat, R* rlon, R* crot, R* srot,
+         i64* ibo, u8* lo, R* go, R* vo, i64& iret) {
+  Runtime& RT = rt();
+  iret = 0;
+  if (!(ip == 0 || ip == 1 || ip == 2 || ip == 3 || ip == 6)) {
+    // ip=4 (spectral) is outside this library's scope; other values make the reference error-stop.
+    fprintf(stderr, "ipb200: interpolation method ip=%lld is not supported (0,1,2,3,6 are)\n", (long long)ip);
+    iret = 1; return;
+  }
+  if (!gin.ok || !gout.ok) { fprintf(stderr, "ipb200: unrecognised grid definition\n"); iret = 1; return; }
+  if (mi >= ((i64)1 << 31) || mo >= ((i64)1 << 31) || km < 0) { iret = 1; return; }
+  std::vector<int> devs;
+  {
+    std::lock_guard<std::mutex> g(RT.mu);
+    RT.last_h2d = 0; RT.last_d2h = 0; RT.last_plan_hit = 0;
+    if (!dev && gout.p.type != P_STATION) devs = RT.shard;
+  }
+  const int nd = (int)std::min<i64>((i64)devs.size(), vec ? km : km / 2);
+  if (nd <= 1) {
+    run_on<R>(devs.size() == 1 ? devs[0] : RT.current_device(), true, vec, dev, user_stream, ip, ipopt, gin, gout, mi, mo, km, ibi, li, gi, vi, no,
+              rlat, rlon, crot, srot, ibo, lo, go, vo, iret);
+    return;
+  }
+  // contiguous field slices (vector pairs stay together: u and v share k); slice 0 also delivers the geometry
+  std::vector<i64> nos(nd, no), irets(nd, 0);
+  std::vector<int> errs(nd, 0);
+  std::vector<std::thread> th;
+  for (int d = 0; d < nd; d++) {
+    const i64 k0 = km * d / nd, k1 = km * (d + 1) / nd;
+    th.emplace_back([&, d, k0, k1]() {
+      try {
+        run_on<R>(devs[d], d == 0, vec, 0, nullptr, ip, ipopt, gin, gout, mi, mo, k1 - k0, ibi + k0, li ? li + (size_t)k0 * mi : nullptr,
+                  gi + (size_t)k0 * mi, vi ? vi + (size_t)k0 * mi : nullptr, nos[d], d == 0 ? rlat : nullptr, d == 0 ? rlon : nullptr,
+                  d == 0 ? crot : nullptr, d == 0 ? srot : nullptr, ibo + k0, lo + (size_t)k0 * mo, go + (size_t)k0 * mo,
+                  vo ? vo + (size_t)k0 * mo : nullptr, irets[d]);
+      } catch (cudaError_t e) { errs[d] = (int)e ? (int)e : 1; } catch (...) { errs[d] = -1; }
+    });
+  }
+  for (auto& t : th) t.join();
+  for (int d = 0; d < nd; d++) {
+    if (errs[d] > 0) throw (cudaError_t)errs[d];
+    if (errs[d] < 0) throw std::runtime_error("ipb200: worker failed");
+  }
+  no = nos[0]; iret = irets[0];
+}
+
+// ---- explicit plan handles and the non-draining apply ------------------------------------------
+struct IntPack { static constexpr int N = 512; int v[N]; };
+static __global__ void k_set_ints(IntPack pk, int n, int* dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = pk.v[i];
+}
+
+template <class R>
+PlanHandle* plan_get(bool vec, i64 ip, const i64* ipopt, const GridHost<R>& gin, const GridHost<R>& gout, i64 mi, i64 mo, i64& no, i64& iret) {
+  Runtime& RT = rt();
+  iret = 0; no = 0;
+  if (!(ip == 0 || ip == 1 || ip == 2 || ip == 3 || ip == 6) || !gin.ok || !gout.ok || gout.p.type == P_STATION ||
+      mi >= ((i64)1 << 31) || mo >= ((i64)1 << 31)) { iret = 1; return nullptr; }
+  const int method = (int)ip;
+  const bool budget = method == M_BUDGET || method == M_NBUDGET;
+  ApplyOpts<R> o;
+  iret = decode_opts<R>(method, ipopt, o);
+  if (!budget && iret != 0) return nullptr;
+  const int device = RT.current_device();
+  DevState& DS = RT.state(device);
+  std::lock_guard<std::mutex> lock(DS.mu);
+  int hit = 0;
+  std::shared_ptr<Plan<R>> P = obtain_plan<R>(DS, method, vec, ipopt, gin, gout, mi, mo, 0, nullptr, nullptr, nullptr, nullptr, false, DS.stream[0], hit);
+  IPB_CUDA(cudaStreamSynchronize(DS.stream[0]));
+  if (budget) { iret = P->iret; o.pmp = ((R)P->bo.mp * IPB_RC(0.01)) * (R)P->bo.nb4; }
+  else if (P->iret != 0) { iret = P->iret; return nullptr; }
+  no = P->no;
+  PlanHandle* h = new PlanHandle();
+  h->kind_bytes = (int)sizeof(R); h->device = device; h->method = method; h->vec = vec; h->plan = std::static_pointer_cast<void>(P);
+  h->mi = mi; h->mo = mo; h->no = P->no; h->iret = iret; h->pmp = (double)o.pmp; h->mcon = o.mcon; h->mspiral = o.mspiral;
+  return h;
+}
+
+// rlat / rlon / crot / srot of the plan's output grid into host or device arrays (any may be null), queued on `stream`
+template <class R> int plan_geometry(PlanHandle* h, void* stream, R* rlat, R* rlon, R* crot, R* srot) {
+  if (!h || h->kind_bytes != (int)sizeof(R)) return 1;
+  DeviceGuard guard(h->device);
+  Plan<R>* P = static_cast<Plan<R>*>(h->plan.get());
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)h->mo * sizeof(R);
+  if (rlat) IPB_CUDA(cudaMemcpyAsync(rlat, P->rlat, n, cudaMemcpyDefault, s));
+  if (rlon) IPB_CUDA(cudaMemcpyAsync(rlon, P->rlon, n, cudaMemcpyDefault, s));
+  if (h->vec && crot) IPB_CUDA(cudaMemcpyAsync(crot, P->crot, n, cudaMemcpyDefault, s));
+  if (h->vec && srot) IPB_CUDA(cudaMemcpyAsync(srot, P->srot, n, cudaMemcpyDefault, s));
+  return 0;
+}
+
+// Queues the apply stage for km device-resident fields on `stream` and returns without waiting: ibi is read from the
+// host before the call returns, d_ibo (km int32 on the device, may be null) receives ibo when the stream gets there.
+template <class R>
+int plan_apply(PlanHandle* h, void* stream, i64 km, const i64* ibi, const u8* li, const R* gi, const R* vi, int* d_ibo, u8* lo, R* go, R* vo) {
+  if (!h || h->kind_bytes != (int)sizeof(R) || km < 0) return 1;
+  if (km == 0 || h->no <= 0) return 0;
+  DeviceGuard guard(h->device);
+  Plan<R>* P = static_cast<Plan<R>*>(h->plan.get());
+  cudaStream_t s = (cudaStream_t)stream;
+  bool any_mask = false;
+  std::vector<int> ibi32((size_t)km);
+  for (i64 k = 0; k < km; k++) { ibi32[k] = ibi[k] != 0 ? (int)ibi[k] : 0; any_mask = any_mask || ibi[k] != 0; }
+  if (any_mask && P->method == M_BILINEAR && !P->vec && !P->gt.ok && !P->gt_tried) {
+    DevState& DS = rt().state(h->device);
+    std::lock_guard<std::mutex> lock(DS.mu);
+    AsyncAlloc scope(s);
+    P->gt_tried = true;
+    build_gtiles<R>(*P, s);
+    P->bytes += P->gt.bytes;
+  }
+  int* d_int = nullptr;   // [ibi | flag | ibo], stream-ordered: freed on the same stream after its last use
+  IPB_CUDA(cudaMallocAsync((void**)&d_int, (size_t)km * 3 * sizeof(int), s));
+  for (i64 k0 = 0; k0 < km; k0 += IntPack::N) {   // ibi travels as kernel arguments: no host buffer outlives the call, no stream drain
+    IntPack pk;
+    const int n = (int)std::min<i64>(IntPack::N, km - k0);
+    for (int i = 0; i < n; i++) pk.v[i] = ibi32[k0 + i];
+    k_set_ints<<<nblk(n, 128), 128, 0, s>>>(pk, n, d_int + k0);
+    g_launches++;
+  }
+  IPB_CUDA(cudaMemsetAsync(d_int + km, 0, (size_t)km * sizeof(int), s));
+  FieldArgs<R> a{(int)h->no, (int)h->mi, (int)h->mo, (int)km, gi, vi, any_mask ? li : nullptr, d_int, go, vo, lo, d_int + km, (R)h->pmp, h->mcon, h->mspiral};
+  launch_apply<R>(*P, h->vec, a, s);
+  launch_post<R>(*P, h->vec, a, d_ibo ? d_ibo : d_int + 2 * km, s);
+  IPB_CUDA(cudaFreeAsync(d_int, s));
+  return 0;
 }
 
 // ---- gdswzd ----------------------------------------------------------------------------------------
@@ -347,8 +498,9 @@ template <class R>
 void run_gdswzd(GridHost<R> gh, i64 iopt, i64 npts, R fill, R* x, R* y, R* rlon, R* rlat, i64& nret, R* crot, R* srot, R* xlon,
                 R* xlat, R* ylon, R* ylat, R* area) {
   Runtime& RT = rt();
-  std::lock_guard<std::mutex> lock(RT.mu);
-  RT.ensure_init();
+  const int device = RT.current_device();
+  DevState& DS = RT.state(device);
+  std::lock_guard<std::mutex> lock(DS.mu);
   if (!gh.ok) { fprintf(stderr, "ipb200: gdswzd: unrecognised grid definition\n"); nret = 0; return; }
   if (npts <= 0) { nret = 0; return; }
   if (gh.p.type == P_STATION) { nret = npts; if (iopt == 0) for (i64 n = 0; n < npts; n++) { x[n] = fill; y[n] = fill; } return; }
@@ -357,7 +509,7 @@ void run_gdswzd(GridHost<R> gh, i64 iopt, i64 npts, R fill, R* x, R* y, R* rlon,
     for (i64 n = 0; n < npts; n++) { rlat[n] = fill; rlon[n] = fill; x[n] = fill; y[n] = fill; }
     return;
   }
-  cudaStream_t st = RT.stream[0];
+  cudaStream_t st = DS.stream[0];
   AsyncAlloc scope(st);
   R* tab = nullptr;
   upload_tables(gh, tab);

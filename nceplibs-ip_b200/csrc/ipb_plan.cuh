@@ -15,10 +15,12 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <memory>
 #include <vector>
 
 #include "ipb_decode.h"
 #include "ipb_proj.cuh"
+#include "ipb_state.h"
 
 namespace ipb {
 
@@ -33,24 +35,23 @@ extern std::atomic<long long> g_launches;  // kernels launched by this library (
     }                                                                                            \
   } while (0)
 
-// Plan arrays are allocated stream-ordered from the device's memory pool while a plan is being built (g_async_alloc
-// set by run(), under the runtime mutex): a plan is ~40 arrays, and cudaMalloc's round trips were most of the 20 ms a
-// first call on a grid pair took; station-point outputs, whose plans are rebuilt on every call, pay it every time.
-extern bool g_async_alloc;
-extern cudaStream_t g_alloc_stream;
+// Plan arrays are allocated stream-ordered from the device's memory pool while a plan is being built (an AsyncAlloc
+// scope of the calling thread, ipb_state.h): a plan is ~40 arrays, and cudaMalloc's round trips were most of the 20 ms
+// a first call on a grid pair took; station-point outputs, whose plans are rebuilt on every call, pay it every time.
 template <class T> T* dalloc(size_t n) {
   T* p = nullptr;
-  if (g_async_alloc) IPB_CUDA(cudaMallocAsync((void**)&p, (n ? n : 1) * sizeof(T), g_alloc_stream));
+  const AllocCtx& c = alloc_ctx();
+  if (c.async) IPB_CUDA(cudaMallocAsync((void**)&p, (n ? n : 1) * sizeof(T), c.stream));
   else IPB_CUDA(cudaMalloc((void**)&p, (n ? n : 1) * sizeof(T)));
   return p;
 }
-// Frees go back to the pool stream-ordered as well: on the building stream while a plan is being built, else on the
-// library's own stream (a plan is only destroyed after every call that used it has synchronised its streams).
-extern cudaStream_t g_free_stream;
+// Frees go back to the pool stream-ordered as well: on the scope's stream (while a plan is built: the building stream;
+// when a plan is destroyed: the owning device's first stream — a plan is only destroyed after every call that used it
+// has synchronised its streams).
 template <class T> void dfree(T*& p) {
   if (p) {
-    if (g_async_alloc) cudaFreeAsync((void*)p, g_alloc_stream);
-    else if (g_free_stream) cudaFreeAsync((void*)p, g_free_stream);
+    const AllocCtx& c = alloc_ctx();
+    if (c.async) cudaFreeAsync((void*)p, c.stream);
     else cudaFree((void*)p);
   }
   p = nullptr;
@@ -132,8 +133,12 @@ template <class R> struct Plan {
   int* bxy = nullptr;                // [no] source cell of every point (iy << 16 | ix), -1 = irregular stencil
   size_t bytes = 0;
   double build_ms = 0;
+  int device = 0;                    // the device the arrays live on, and the stream their frees are ordered on
+  cudaStream_t free_stream = nullptr;
 
   ~Plan() {
+    DeviceGuard guard(device);
+    AsyncAlloc scope(free_stream);
     dfree(d_tab_in); dfree(d_tab_out); dfree(rlat); dfree(rlon); dfree(crot); dfree(srot); dfree(x); dfree(y);
     dfree(nxy); dfree(wxy); dfree(cxy); dfree(sxy); dfree(nc); dfree(bn); dfree(bw); dfree(bc); dfree(bs); dfree(d_wb); dfree(cn); dfree(cw); dfree(cwsum);
     dfree(pole_n); dfree(pole_s); dfree(pclon_n); dfree(pslon_n); dfree(pclon_s); dfree(pslon_s);
@@ -413,7 +418,7 @@ template <class R> void upload_tables(GridHost<R>& gh, R*& dptr) {
   dptr = dalloc<R>(3 * n);
   // on the allocating stream (the array is stream-ordered); the host vectors are pageable, so each copy has left the
   // host buffer when the call returns
-  cudaStream_t st = g_async_alloc ? g_alloc_stream : (cudaStream_t)0;
+  cudaStream_t st = alloc_ctx().async ? alloc_ctx().stream : (cudaStream_t)0;
   IPB_CUDA(cudaMemcpyAsync(dptr, gh.alat.data(), n * sizeof(R), cudaMemcpyHostToDevice, st));
   IPB_CUDA(cudaMemcpyAsync(dptr + n, gh.blat.data(), n * sizeof(R), cudaMemcpyHostToDevice, st));
   IPB_CUDA(cudaMemcpyAsync(dptr + 2 * n, gh.ylat_row.data(), n * sizeof(R), cudaMemcpyHostToDevice, st));
@@ -432,10 +437,11 @@ template <class R>
 Plan<R>* build_plan(int method, bool vec, const i64* ipopt, const GridHost<R>& gin_h, const GridHost<R>& gout_h, i64 mi,
                     i64 mo, i64 no_in, const R* st_lat, const R* st_lon, const R* st_crot, const R* st_srot,
                     cudaStream_t st) {
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0); cudaEventCreate(&e1);
-  cudaEventRecord(e0, st);
-  Plan<R>* P = new Plan<R>();
+  struct Ev { cudaEvent_t e = nullptr; Ev() { cudaEventCreate(&e); } ~Ev() { if (e) cudaEventDestroy(e); } } e0, e1;   // released on every path
+  cudaEventRecord(e0.e, st);
+  std::unique_ptr<Plan<R>> holder(new Plan<R>());   // a CUDA failure below throws: the plan and its device arrays go with it
+  Plan<R>* P = holder.get();
+  cudaGetDevice(&P->device); P->free_stream = st;
   P->method = method; P->vec = vec;
   P->gin = gin_h; P->gout = gout_h;
   upload_tables(P->gin, P->d_tab_in);
@@ -598,13 +604,12 @@ Plan<R>* build_plan(int method, bool vec, const i64* ipopt, const GridHost<R>& g
     }
   }
   P->iret = iret;
-  cudaEventRecord(e1, st);
-  cudaEventSynchronize(e1);
+  cudaEventRecord(e1.e, st);
+  cudaEventSynchronize(e1.e);
   float ms = 0;
-  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventElapsedTime(&ms, e0.e, e1.e);
   P->build_ms = ms;
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
-  return P;
+  return holder.release();
 }
 
 }  // namespace ipb
