@@ -9,8 +9,8 @@
 !! the kind suffix (include/ipb200.h).  Build once per kind exactly like the reference does
 !! (src/CMakeLists.txt:36-76):
 !!
-!!   gfortran -cpp -DLSIZE=4 -c ip_mod.F90                              -> libip_4  (INTEGER(4), REAL(4))
-!!   gfortran -cpp -DLSIZE=D -fdefault-real-8 -c ip_mod.F90             -> libip_d  (INTEGER(4), REAL(8))
+!!   gfortran -cpp -ffree-line-length-none -DLSIZE=4 -c ip_mod.F90                        -> libip_4  (INTEGER(4), REAL(4))
+!!   gfortran -cpp -ffree-line-length-none -DLSIZE=D -fdefault-real-8 -c ip_mod.F90           -> libip_d  (INTEGER(4), REAL(8))
 !!   gfortran -cpp -DLSIZE=8 -fdefault-real-8 -fdefault-integer-8 ...   -> libip_8  (INTEGER(8), REAL(8))
 !!
 !! and link with -lipb200 -lcudart.  The specific routines keep the reference's bind(c) names
@@ -65,53 +65,65 @@ module ipb200_c
   use iso_c_binding
   implicit none
   interface
-     subroutine c_ipolates_grib2(ip,ipopt,igdtnumi,igdtmpli,igdtleni,igdtnumo,igdtmplo,igdtleno, &
+     subroutine c_ipolates_grib2(ip,ipopt,igdtnumi,igdtmpli,igdtleni,igdtnumo,igdtmplo, &
+          igdtleno, &
           mi,mo,km,ibi,li,gi,no,rlat,rlon,ibo,lo,go,iret) bind(c, name=IPB_N_S2)
        import
-       IPB_INT :: ip, ipopt(20), igdtnumi, igdtmpli(*), igdtleni, igdtnumo, igdtmplo(*), igdtleno, mi, mo, km, ibi(*)
+       IPB_INT :: ip, ipopt(20), igdtnumi, igdtmpli(*), igdtleni, igdtnumo, igdtmplo(*), &
+            igdtleno, mi, mo, km, ibi(*)
        logical(c_bool) :: li(*), lo(*)
        IPB_REAL :: gi(*), rlat(*), rlon(*), go(*)
        IPB_INT :: no, ibo(*), iret
      end subroutine c_ipolates_grib2
-     subroutine c_ipolates_grib2_sf(ip,ipopt,igdtnumi,igdtmpli,igdtleni,igdtnumo,igdtmplo,igdtleno, &
+     subroutine c_ipolates_grib2_sf(ip,ipopt,igdtnumi,igdtmpli,igdtleni,igdtnumo,igdtmplo, &
+          igdtleno, &
           mi,mo,km,ibi,li,gi,no,rlat,rlon,ibo,lo,go,iret) bind(c, name=IPB_N_S2F)
        import
-       IPB_INT :: ip, ipopt(20), igdtnumi, igdtmpli(*), igdtleni, igdtnumo, igdtmplo(*), igdtleno, mi, mo, km, ibi
+       IPB_INT :: ip, ipopt(20), igdtnumi, igdtmpli(*), igdtleni, igdtnumo, igdtmplo(*), &
+            igdtleno, mi, mo, km, ibi
        logical(c_bool) :: li(*), lo(*)
        IPB_REAL :: gi(*), rlat(*), rlon(*), go(*)
        IPB_INT :: no, ibo, iret
      end subroutine c_ipolates_grib2_sf
-     subroutine c_ipolates_grib1(ip,ipopt,kgdsi,kgdso,mi,mo,km,ibi,li,gi,no,rlat,rlon,ibo,lo,go,iret) bind(c, name=IPB_N_S1)
+     subroutine c_ipolates_grib1(ip,ipopt,kgdsi,kgdso,mi,mo,km,ibi,li,gi,no,rlat,rlon,ibo, &
+          lo,go,iret) bind(c, name=IPB_N_S1)
        import
        IPB_INT :: ip, ipopt(20), kgdsi(200), kgdso(200), mi, mo, km, ibi(*)
        logical(c_bool) :: li(*), lo(*)
        IPB_REAL :: gi(*), rlat(*), rlon(*), go(*)
        IPB_INT :: no, ibo(*), iret
      end subroutine c_ipolates_grib1
-     subroutine c_ipolates_grib1_sf(ip,ipopt,kgdsi,kgdso,mi,mo,km,ibi,li,gi,no,rlat,rlon,ibo,lo,go,iret) bind(c, name=IPB_N_S1F)
+     subroutine c_ipolates_grib1_sf(ip,ipopt,kgdsi,kgdso,mi,mo,km,ibi,li,gi,no,rlat,rlon, &
+          ibo,lo,go,iret) bind(c, name=IPB_N_S1F)
        import
        IPB_INT :: ip, ipopt(20), kgdsi(200), kgdso(200), mi, mo, km, ibi
        logical(c_bool) :: li(*), lo(*)
        IPB_REAL :: gi(*), rlat(*), rlon(*), go(*)
        IPB_INT :: no, ibo, iret
      end subroutine c_ipolates_grib1_sf
-     subroutine c_ipolatev_grib2(ip,ipopt,igdtnumi,igdtmpli,igdtleni,igdtnumo,igdtmplo,igdtleno, &
+     subroutine c_ipolatev_grib2(ip,ipopt,igdtnumi,igdtmpli,igdtleni,igdtnumo,igdtmplo, &
+          igdtleno, &
           mi,mo,km,ibi,li,ui,vi,no,rlat,rlon,crot,srot,ibo,lo,uo,vo,iret) bind(c, name=IPB_N_V2)
        import
-       IPB_INT :: ip, ipopt(20), igdtnumi, igdtmpli(*), igdtleni, igdtnumo, igdtmplo(*), igdtleno, mi, mo, km, ibi(*)
+       IPB_INT :: ip, ipopt(20), igdtnumi, igdtmpli(*), igdtleni, igdtnumo, igdtmplo(*), &
+            igdtleno, mi, mo, km, ibi(*)
        logical(c_bool) :: li(*), lo(*)
        IPB_REAL :: ui(*), vi(*), rlat(*), rlon(*), crot(*), srot(*), uo(*), vo(*)
        IPB_INT :: no, ibo(*), iret
      end subroutine c_ipolatev_grib2
-     subroutine c_ipolatev_grib2_sf(ip,ipopt,igdtnumi,igdtmpli,igdtleni,igdtnumo,igdtmplo,igdtleno, &
-          mi,mo,km,ibi,li,ui,vi,no,rlat,rlon,crot,srot,ibo,lo,uo,vo,iret) bind(c, name=IPB_N_V2F)
+     subroutine c_ipolatev_grib2_sf(ip,ipopt,igdtnumi,igdtmpli,igdtleni,igdtnumo,igdtmplo, &
+          igdtleno, &
+          mi,mo,km,ibi,li,ui,vi,no,rlat,rlon,crot,srot,ibo,lo,uo,vo,iret) bind(c, &
+               name=IPB_N_V2F)
        import
-       IPB_INT :: ip, ipopt(20), igdtnumi, igdtmpli(*), igdtleni, igdtnumo, igdtmplo(*), igdtleno, mi, mo, km, ibi
+       IPB_INT :: ip, ipopt(20), igdtnumi, igdtmpli(*), igdtleni, igdtnumo, igdtmplo(*), &
+            igdtleno, mi, mo, km, ibi
        logical(c_bool) :: li(*), lo(*)
        IPB_REAL :: ui(*), vi(*), rlat(*), rlon(*), crot(*), srot(*), uo(*), vo(*)
        IPB_INT :: no, ibo, iret
      end subroutine c_ipolatev_grib2_sf
-     subroutine c_ipolatev_grib1(ip,ipopt,kgdsi,kgdso,mi,mo,km,ibi,li,ui,vi,no,rlat,rlon,crot,srot,ibo,lo,uo,vo,iret) &
+     subroutine c_ipolatev_grib1(ip,ipopt,kgdsi,kgdso,mi,mo,km,ibi,li,ui,vi,no,rlat,rlon, &
+          crot,srot,ibo,lo,uo,vo,iret) &
           bind(c, name=IPB_N_V1)
        import
        IPB_INT :: ip, ipopt(20), kgdsi(200), kgdso(200), mi, mo, km, ibi(*)
@@ -119,7 +131,8 @@ module ipb200_c
        IPB_REAL :: ui(*), vi(*), rlat(*), rlon(*), crot(*), srot(*), uo(*), vo(*)
        IPB_INT :: no, ibo(*), iret
      end subroutine c_ipolatev_grib1
-     subroutine c_ipolatev_grib1_sf(ip,ipopt,kgdsi,kgdso,mi,mo,km,ibi,li,ui,vi,no,rlat,rlon,crot,srot,ibo,lo,uo,vo,iret) &
+     subroutine c_ipolatev_grib1_sf(ip,ipopt,kgdsi,kgdso,mi,mo,km,ibi,li,ui,vi,no,rlat,rlon, &
+          crot,srot,ibo,lo,uo,vo,iret) &
           bind(c, name=IPB_N_V1F)
        import
        IPB_INT :: ip, ipopt(20), kgdsi(200), kgdso(200), mi, mo, km, ibi
@@ -152,7 +165,8 @@ end module ipb200_c
 !> Mirror of src/ip_interpolators_mod.F90:17-27.
 module ip_interpolators_mod
   implicit none
-  integer, parameter, public :: BILINEAR_INTERP_ID = 0, BICUBIC_INTERP_ID = 1, NEIGHBOR_INTERP_ID = 2, &
+  integer, parameter, public :: BILINEAR_INTERP_ID = 0, BICUBIC_INTERP_ID = 1, &
+       NEIGHBOR_INTERP_ID = 2, &
        BUDGET_INTERP_ID = 3, SPECTRAL_INTERP_ID = 4, NEIGHBOR_BUDGET_INTERP_ID = 6
 end module ip_interpolators_mod
 
@@ -162,7 +176,8 @@ module ipolates_mod
   use ipb200_c
   implicit none
   private
-  public :: ipolates, ipolates_grib2, ipolates_grib1_single_field, ipolates_grib1, ipolates_grib2_single_field
+  public :: ipolates, ipolates_grib2, ipolates_grib1_single_field, ipolates_grib1, &
+       ipolates_grib2_single_field
   interface ipolates
      module procedure ipolates_grib1
      module procedure ipolates_grib1_single_field
@@ -172,7 +187,8 @@ module ipolates_mod
 contains
   subroutine ipolates_grib2(ip,ipopt,igdtnumi,igdtmpli,igdtleni,igdtnumo,igdtmplo,igdtleno, &
        mi,mo,km,ibi,li,gi,no,rlat,rlon,ibo,lo,go,iret) bind(c)       ! src/ipolates.F90:587-636
-    IPB_INT, intent(in) :: ip, ipopt(20), km, mi, mo, ibi(km), igdtnumi, igdtleni, igdtmpli(igdtleni)
+    IPB_INT, intent(in) :: ip, ipopt(20), km, mi, mo, ibi(km), igdtnumi, igdtleni, &
+         igdtmpli(igdtleni)
     IPB_INT, intent(in) :: igdtnumo, igdtleno, igdtmplo(igdtleno)
     IPB_INT, intent(out) :: no, iret, ibo(km)
     logical(c_bool), intent(in) :: li(mi,km)
@@ -183,9 +199,11 @@ contains
     call c_ipolates_grib2(ip,ipopt,igdtnumi,igdtmpli,igdtleni,igdtnumo,igdtmplo,igdtleno, &
          mi,mo,km,ibi,li,gi,no,rlat,rlon,ibo,lo,go,iret)
   end subroutine ipolates_grib2
-  subroutine ipolates_grib2_single_field(ip,ipopt,igdtnumi,igdtmpli,igdtleni,igdtnumo,igdtmplo,igdtleno, &
+  subroutine ipolates_grib2_single_field(ip,ipopt,igdtnumi,igdtmpli,igdtleni,igdtnumo, &
+       igdtmplo,igdtleno, &
        mi,mo,km,ibi,li,gi,no,rlat,rlon,ibo,lo,go,iret) bind(c)       ! src/ipolates.F90:808-864
-    IPB_INT, intent(in) :: ip, ipopt(20), km, mi, mo, ibi, igdtnumi, igdtleni, igdtmpli(igdtleni)
+    IPB_INT, intent(in) :: ip, ipopt(20), km, mi, mo, ibi, igdtnumi, igdtleni, &
+         igdtmpli(igdtleni)
     IPB_INT, intent(in) :: igdtnumo, igdtleno, igdtmplo(igdtleno)
     IPB_INT, intent(out) :: no, iret, ibo
     logical(c_bool), intent(in) :: li(mi)
@@ -196,7 +214,8 @@ contains
     call c_ipolates_grib2_sf(ip,ipopt,igdtnumi,igdtmpli,igdtleni,igdtnumo,igdtmplo,igdtleno, &
          mi,mo,km,ibi,li,gi,no,rlat,rlon,ibo,lo,go,iret)
   end subroutine ipolates_grib2_single_field
-  subroutine ipolates_grib1(ip,ipopt,kgdsi,kgdso,mi,mo,km,ibi,li,gi,no,rlat,rlon,ibo,lo,go,iret) bind(c)  ! :293-334
+  subroutine ipolates_grib1(ip,ipopt,kgdsi,kgdso,mi,mo,km,ibi,li,gi,no,rlat,rlon,ibo,lo,go, &
+       iret) bind(c)  ! :293-334
     IPB_INT, intent(in) :: ip, ipopt(20), km, mi, mo, ibi(km), kgdsi(200), kgdso(200)
     IPB_INT, intent(out) :: no, iret, ibo(km)
     logical(c_bool), intent(in) :: li(mi,km)
@@ -206,7 +225,8 @@ contains
     IPB_REAL, intent(out) :: go(mo,km)
     call c_ipolates_grib1(ip,ipopt,kgdsi,kgdso,mi,mo,km,ibi,li,gi,no,rlat,rlon,ibo,lo,go,iret)
   end subroutine ipolates_grib1
-  subroutine ipolates_grib1_single_field(ip,ipopt,kgdsi,kgdso,mi,mo,km,ibi,li,gi,no,rlat,rlon,ibo,lo,go,iret) bind(c)  ! :158-206
+  subroutine ipolates_grib1_single_field(ip,ipopt,kgdsi,kgdso,mi,mo,km,ibi,li,gi,no,rlat, &
+       rlon,ibo,lo,go,iret) bind(c)  ! :158-206
     IPB_INT, intent(in) :: ip, ipopt(20), km, mi, mo, ibi, kgdsi(200), kgdso(200)
     IPB_INT, intent(out) :: no, iret, ibo
     logical(c_bool), intent(in) :: li(mi)
@@ -214,7 +234,8 @@ contains
     IPB_REAL, intent(in) :: gi(mi)
     IPB_REAL, intent(inout) :: rlat(mo), rlon(mo)
     IPB_REAL, intent(out) :: go(mo)
-    call c_ipolates_grib1_sf(ip,ipopt,kgdsi,kgdso,mi,mo,km,ibi,li,gi,no,rlat,rlon,ibo,lo,go,iret)
+    call c_ipolates_grib1_sf(ip,ipopt,kgdsi,kgdso,mi,mo,km,ibi,li,gi,no,rlat,rlon,ibo,lo,go, &
+         iret)
   end subroutine ipolates_grib1_single_field
 end module ipolates_mod
 
@@ -224,7 +245,8 @@ module ipolatev_mod
   use ipb200_c
   implicit none
   private
-  public :: ipolatev, ipolatev_grib2, ipolatev_grib1_single_field, ipolatev_grib1, ipolatev_grib2_single_field
+  public :: ipolatev, ipolatev_grib2, ipolatev_grib1_single_field, ipolatev_grib1, &
+       ipolatev_grib2_single_field
   interface ipolatev
      module procedure ipolatev_grib1
      module procedure ipolatev_grib1_single_field
@@ -233,8 +255,10 @@ module ipolatev_mod
   end interface ipolatev
 contains
   subroutine ipolatev_grib2(ip,ipopt,igdtnumi,igdtmpli,igdtleni,igdtnumo,igdtmplo,igdtleno, &
-       mi,mo,km,ibi,li,ui,vi,no,rlat,rlon,crot,srot,ibo,lo,uo,vo,iret) bind(c)      ! src/ipolatev.F90:382-434
-    IPB_INT, intent(in) :: ip, ipopt(20), km, mi, mo, ibi(km), igdtnumi, igdtleni, igdtmpli(igdtleni)
+       mi,mo,km,ibi,li,ui,vi,no,rlat,rlon,crot,srot,ibo,lo,uo,vo, &
+            iret) bind(c)      ! src/ipolatev.F90:382-434
+    IPB_INT, intent(in) :: ip, ipopt(20), km, mi, mo, ibi(km), igdtnumi, igdtleni, &
+         igdtmpli(igdtleni)
     IPB_INT, intent(in) :: igdtnumo, igdtleno, igdtmplo(igdtleno)
     IPB_INT, intent(out) :: no, iret, ibo(km)
     logical(c_bool), intent(in) :: li(mi,km)
@@ -245,9 +269,12 @@ contains
     call c_ipolatev_grib2(ip,ipopt,igdtnumi,igdtmpli,igdtleni,igdtnumo,igdtmplo,igdtleno, &
          mi,mo,km,ibi,li,ui,vi,no,rlat,rlon,crot,srot,ibo,lo,uo,vo,iret)
   end subroutine ipolatev_grib2
-  subroutine ipolatev_grib2_single_field(ip,ipopt,igdtnumi,igdtmpli,igdtleni,igdtnumo,igdtmplo,igdtleno, &
-       mi,mo,km,ibi,li,ui,vi,no,rlat,rlon,crot,srot,ibo,lo,uo,vo,iret) bind(c)      ! src/ipolatev.F90:832-891
-    IPB_INT, intent(in) :: ip, ipopt(20), km, mi, mo, ibi, igdtnumi, igdtleni, igdtmpli(igdtleni)
+  subroutine ipolatev_grib2_single_field(ip,ipopt,igdtnumi,igdtmpli,igdtleni,igdtnumo, &
+       igdtmplo,igdtleno, &
+       mi,mo,km,ibi,li,ui,vi,no,rlat,rlon,crot,srot,ibo,lo,uo,vo, &
+            iret) bind(c)      ! src/ipolatev.F90:832-891
+    IPB_INT, intent(in) :: ip, ipopt(20), km, mi, mo, ibi, igdtnumi, igdtleni, &
+         igdtmpli(igdtleni)
     IPB_INT, intent(in) :: igdtnumo, igdtleno, igdtmplo(igdtleno)
     IPB_INT, intent(out) :: no, iret, ibo
     logical(c_bool), intent(in) :: li(mi)
@@ -260,7 +287,8 @@ contains
   end subroutine ipolatev_grib2_single_field
   !> The reference temporarily ORs 256 into kgds(11) for grid 203 (src/ipolatev.F90:602-626, hence
   !! intent(inout)); libipb200 applies that switch on its own copy and leaves the caller's arrays alone.
-  subroutine ipolatev_grib1(ip,ipopt,kgdsi,kgdso,mi,mo,km,ibi,li,ui,vi,no,rlat,rlon,crot,srot,ibo,lo,uo,vo,iret) bind(c)  ! :565-628
+  subroutine ipolatev_grib1(ip,ipopt,kgdsi,kgdso,mi,mo,km,ibi,li,ui,vi,no,rlat,rlon,crot, &
+       srot,ibo,lo,uo,vo,iret) bind(c)  ! :565-628
     IPB_INT, intent(in) :: ip, ipopt(20), km, mi, mo, ibi(km)
     IPB_INT, intent(inout) :: kgdsi(200), kgdso(200)
     IPB_INT, intent(out) :: no, iret, ibo(km)
@@ -269,9 +297,11 @@ contains
     IPB_REAL, intent(in) :: ui(mi,km), vi(mi,km)
     IPB_REAL, intent(inout) :: rlat(mo), rlon(mo), crot(mo), srot(mo)
     IPB_REAL, intent(out) :: uo(mo,km), vo(mo,km)
-    call c_ipolatev_grib1(ip,ipopt,kgdsi,kgdso,mi,mo,km,ibi,li,ui,vi,no,rlat,rlon,crot,srot,ibo,lo,uo,vo,iret)
+    call c_ipolatev_grib1(ip,ipopt,kgdsi,kgdso,mi,mo,km,ibi,li,ui,vi,no,rlat,rlon,crot,srot, &
+         ibo,lo,uo,vo,iret)
   end subroutine ipolatev_grib1
-  subroutine ipolatev_grib1_single_field(ip,ipopt,kgdsi,kgdso,mi,mo,km,ibi,li,ui,vi,no,rlat,rlon,crot,srot,ibo,lo,uo,vo,iret) &
+  subroutine ipolatev_grib1_single_field(ip,ipopt,kgdsi,kgdso,mi,mo,km,ibi,li,ui,vi,no,rlat, &
+       rlon,crot,srot,ibo,lo,uo,vo,iret) &
        bind(c)                                                                    ! src/ipolatev.F90:680-750
     IPB_INT, intent(in) :: ip, ipopt(20), km, mi, mo, ibi
     IPB_INT, intent(inout) :: kgdsi(200), kgdso(200)
@@ -281,7 +311,8 @@ contains
     IPB_REAL, intent(in) :: ui(mi), vi(mi)
     IPB_REAL, intent(inout) :: rlat(mo), rlon(mo), crot(mo), srot(mo)
     IPB_REAL, intent(out) :: uo(mo), vo(mo)
-    call c_ipolatev_grib1_sf(ip,ipopt,kgdsi,kgdso,mi,mo,km,ibi,li,ui,vi,no,rlat,rlon,crot,srot,ibo,lo,uo,vo,iret)
+    call c_ipolatev_grib1_sf(ip,ipopt,kgdsi,kgdso,mi,mo,km,ibi,li,ui,vi,no,rlat,rlon,crot, &
+         srot,ibo,lo,uo,vo,iret)
   end subroutine ipolatev_grib1_single_field
 end module ipolatev_mod
 
@@ -301,25 +332,33 @@ module gdswzd_mod
   end interface gdswzd
 contains
   subroutine gdswzd_1d_array(igdtnum,igdtmpl,igdtlen,iopt,npts,fill,xpts,ypts,rlon,rlat,nret, &
-       crot,srot,xlon,xlat,ylon,ylat,area)                                       ! src/gdswzd_mod.F90:665-690
+       crot,srot,xlon,xlat,ylon,ylat, &
+            area)                                       ! src/gdswzd_mod.F90:665-690
     integer, intent(in) :: igdtnum, igdtlen, igdtmpl(igdtlen), iopt, npts
     integer, intent(out) :: nret
     real, intent(in) :: fill
     real, intent(inout) :: rlon(npts), rlat(npts), xpts(npts), ypts(npts)
-    real, optional, intent(out) :: crot(npts), srot(npts), xlon(npts), xlat(npts), ylon(npts), ylat(npts), area(npts)
-    call c_gdswzd(igdtnum,igdtmpl,igdtlen,iopt,npts,fill,xpts,ypts,rlon,rlat,nret,crot,srot,xlon,xlat,ylon,ylat,area)
+    real, optional, intent(out) :: crot(npts), srot(npts), xlon(npts), xlat(npts), &
+         ylon(npts), ylat(npts), area(npts)
+    call c_gdswzd(igdtnum,igdtmpl,igdtlen,iopt,npts,fill,xpts,ypts,rlon,rlat,nret,crot,srot, &
+         xlon,xlat,ylon,ylat,area)
   end subroutine gdswzd_1d_array
   subroutine gdswzd_2d_array(igdtnum,igdtmpl,igdtlen,iopt,npts,fill,xpts,ypts,rlon,rlat,nret, &
-       crot,srot,xlon,xlat,ylon,ylat,area)                                       ! src/gdswzd_mod.F90:459-481
+       crot,srot,xlon,xlat,ylon,ylat, &
+            area)                                       ! src/gdswzd_mod.F90:459-481
     integer, intent(in) :: igdtnum, igdtlen, igdtmpl(igdtlen), iopt, npts
     integer, intent(out) :: nret
     real, intent(in) :: fill
-    real, intent(inout) :: rlon(:,:), rlat(:,:), xpts(:,:), ypts(:,:)    ! contiguous, npts elements in all
-    real, optional, intent(out) :: crot(:,:), srot(:,:), xlon(:,:), xlat(:,:), ylon(:,:), ylat(:,:), area(:,:)
-    call c_gdswzd(igdtnum,igdtmpl,igdtlen,iopt,npts,fill,xpts,ypts,rlon,rlat,nret,crot,srot,xlon,xlat,ylon,ylat,area)
+    real, intent(inout) :: rlon(:,:), rlat(:,:), xpts(:,:), ypts(:,:)    ! contiguous, &
+         npts elements in all
+    real, optional, intent(out) :: crot(:,:), srot(:,:), xlon(:,:), xlat(:,:), ylon(:,:), &
+         ylat(:,:), area(:,:)
+    call c_gdswzd(igdtnum,igdtmpl,igdtlen,iopt,npts,fill,xpts,ypts,rlon,rlat,nret,crot,srot, &
+         xlon,xlat,ylon,ylat,area)
   end subroutine gdswzd_2d_array
   subroutine gdswzd_scalar(igdtnum,igdtmpl,igdtlen,iopt,npts,fill,xpts,ypts,rlon,rlat,nret, &
-       crot,srot,xlon,xlat,ylon,ylat,area)                                       ! src/gdswzd_mod.F90:278-381
+       crot,srot,xlon,xlat,ylon,ylat, &
+            area)                                       ! src/gdswzd_mod.F90:278-381
     integer, intent(in) :: igdtnum, igdtlen, igdtmpl(igdtlen), iopt, npts
     integer, intent(out) :: nret
     real, intent(in) :: fill
@@ -327,7 +366,8 @@ contains
     real, optional, intent(out) :: crot, srot, xlon, xlat, ylon, ylat, area
     real :: x1(1), y1(1), lo1(1), la1(1), e(1,7)
     x1 = xpts; y1 = ypts; lo1 = rlon; la1 = rlat
-    call c_gdswzd(igdtnum,igdtmpl,igdtlen,iopt,1,fill,x1,y1,lo1,la1,nret,e(:,1),e(:,2),e(:,3),e(:,4),e(:,5),e(:,6),e(:,7))
+    call c_gdswzd(igdtnum,igdtmpl,igdtlen,iopt,1,fill,x1,y1,lo1,la1,nret,e(:,1),e(:,2),e(:, &
+         3),e(:,4),e(:,5),e(:,6),e(:,7))
     xpts = x1(1); ypts = y1(1); rlon = lo1(1); rlat = la1(1)
     if (present(crot)) crot = e(1,1)
     if (present(srot)) srot = e(1,2)
@@ -337,21 +377,27 @@ contains
     if (present(ylat)) ylat = e(1,6)
     if (present(area)) area = e(1,7)
   end subroutine gdswzd_scalar
-  subroutine gdswzd_grib1(kgds,iopt,npts,fill,xpts,ypts,rlon,rlat,nret,crot,srot,xlon,xlat,ylon,ylat,area)  ! :758-781
+  subroutine gdswzd_grib1(kgds,iopt,npts,fill,xpts,ypts,rlon,rlat,nret,crot,srot,xlon,xlat, &
+       ylon,ylat,area)  ! :758-781
     integer, intent(in) :: kgds(200), iopt, npts
     integer, intent(out) :: nret
     real, intent(in) :: fill
     real, intent(inout) :: rlon(npts), rlat(npts), xpts(npts), ypts(npts)
-    real, optional, intent(out) :: crot(npts), srot(npts), xlon(npts), xlat(npts), ylon(npts), ylat(npts), area(npts)
-    call c_gdswzd_grib1(kgds,iopt,npts,fill,xpts,ypts,rlon,rlat,nret,crot,srot,xlon,xlat,ylon,ylat,area)
+    real, optional, intent(out) :: crot(npts), srot(npts), xlon(npts), xlat(npts), &
+         ylon(npts), ylat(npts), area(npts)
+    call c_gdswzd_grib1(kgds,iopt,npts,fill,xpts,ypts,rlon,rlat,nret,crot,srot,xlon,xlat, &
+         ylon,ylat,area)
   end subroutine gdswzd_grib1
-  subroutine gdswzd_2d_array_grib1(kgds,iopt,npts,fill,xpts,ypts,rlon,rlat,nret,crot,srot,xlon,xlat,ylon,ylat,area)  ! :850-875
+  subroutine gdswzd_2d_array_grib1(kgds,iopt,npts,fill,xpts,ypts,rlon,rlat,nret,crot,srot, &
+       xlon,xlat,ylon,ylat,area)  ! :850-875
     integer, intent(in) :: kgds(200), iopt, npts
     integer, intent(out) :: nret
     real, intent(in) :: fill
     real, intent(inout) :: rlon(:,:), rlat(:,:), xpts(:,:), ypts(:,:)
-    real, optional, intent(out) :: crot(:,:), srot(:,:), xlon(:,:), xlat(:,:), ylon(:,:), ylat(:,:), area(:,:)
-    call c_gdswzd_grib1(kgds,iopt,npts,fill,xpts,ypts,rlon,rlat,nret,crot,srot,xlon,xlat,ylon,ylat,area)
+    real, optional, intent(out) :: crot(:,:), srot(:,:), xlon(:,:), xlat(:,:), ylon(:,:), &
+         ylat(:,:), area(:,:)
+    call c_gdswzd_grib1(kgds,iopt,npts,fill,xpts,ypts,rlon,rlat,nret,crot,srot,xlon,xlat, &
+         ylon,ylat,area)
   end subroutine gdswzd_2d_array_grib1
 end module gdswzd_mod
 
@@ -376,8 +422,10 @@ subroutine gdswzd_c(igdtnum,igdtmpl,igdtlen,iopt,npts,fill,xpts,ypts,rlon,rlat,n
   IPB_INT, intent(out) :: nret
   IPB_REAL, value, intent(in) :: fill
   IPB_REAL, intent(inout) :: xpts(npts), ypts(npts), rlon(npts), rlat(npts)
-  IPB_REAL, intent(out) :: crot(npts), srot(npts), xlon(npts), xlat(npts), ylon(npts), ylat(npts), area(npts)
-  call c_gdswzd(igdtnum,igdtmpl,igdtlen,iopt,npts,fill,xpts,ypts,rlon,rlat,nret,crot,srot,xlon,xlat,ylon,ylat,area)
+  IPB_REAL, intent(out) :: crot(npts), srot(npts), xlon(npts), xlat(npts), ylon(npts), &
+       ylat(npts), area(npts)
+  call c_gdswzd(igdtnum,igdtmpl,igdtlen,iopt,npts,fill,xpts,ypts,rlon,rlat,nret,crot,srot, &
+       xlon,xlat,ylon,ylat,area)
 end subroutine gdswzd_c
 
 subroutine gdswzd_c_grib1(kgds,iopt,npts,fill,xpts,ypts,rlon,rlat,nret, &
@@ -390,6 +438,8 @@ subroutine gdswzd_c_grib1(kgds,iopt,npts,fill,xpts,ypts,rlon,rlat,nret, &
   IPB_INT, intent(out) :: nret
   IPB_REAL, value, intent(in) :: fill
   IPB_REAL, intent(inout) :: xpts(npts), ypts(npts), rlon(npts), rlat(npts)
-  IPB_REAL, intent(out) :: crot(npts), srot(npts), xlon(npts), xlat(npts), ylon(npts), ylat(npts), area(npts)
-  call c_gdswzd_grib1(kgds,iopt,npts,fill,xpts,ypts,rlon,rlat,nret,crot,srot,xlon,xlat,ylon,ylat,area)
+  IPB_REAL, intent(out) :: crot(npts), srot(npts), xlon(npts), xlat(npts), ylon(npts), &
+       ylat(npts), area(npts)
+  call c_gdswzd_grib1(kgds,iopt,npts,fill,xpts,ypts,rlon,rlat,nret,crot,srot,xlon,xlat,ylon, &
+       ylat,area)
 end subroutine gdswzd_c_grib1

@@ -127,7 +127,11 @@ k_budget_collapsed(FieldArgs<R> a, int kpb, int nsamp, const int* __restrict__ c
       for (int u = 0; u < U; u++) mb |= (__ldg(l + s_off[u][tid]) ? 1u : 0u) << u;
     }
     // bitmaps are spatially coherent: most warps see all of their taps unmasked and take the plain path
-    if (__all_sync(__activemask(), mb == (1u << U) - 1u)) {
+    // (a field WITH a bitmap accumulates WB*W per tap in floating point even when every tap is usable: next to the
+    // threshold — mp = 100 — that sum, not the integer sum of the sample weights, decides lo: exact path below)
+    const R dpl = wplain - pmp;
+    const bool near_plain = masked && (dpl < 0 ? -dpl : dpl) <= pmp * (R)1e-9;
+    if (__all_sync(__activemask(), mb == (1u << U) - 1u && !near_plain)) {
 #pragma unroll
       for (int u = 0; u < U; u++) acc = acc + s_w[u][tid] * v[u];
       const bool good = wplain >= pmp;
@@ -144,7 +148,7 @@ k_budget_collapsed(FieldArgs<R> a, int kpb, int nsamp, const int* __restrict__ c
         if ((mb >> u) & 1u) { acc = acc + wu * v[u]; wo = wo + wu; }
       }
       const R d = wo - pmp;
-      if ((d < 0 ? -d : d) <= pmp * (R)1e-9) acc = budget_exact_point<R>(g, l, no, n, true, nsamp, bn, bw, wbs, wo);
+      if (near_plain || (d < 0 ? -d : d) <= pmp * (R)1e-9) acc = budget_exact_point<R>(g, l, no, n, masked, nsamp, bn, bw, wbs, wo);
     }
     const bool good = wo >= pmp;
     __stcs(go, good ? acc / wo : (R)0);

@@ -498,9 +498,12 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
           R wo = 0;
 #pragma unroll
           for (int u = 0; u < U; u++) if ((mbp[u >> 2] >> (8 * (u & 3))) & 1u) wo = wo + w[u];
-          const R d = wo - a.pmp;
           ones_c = (allm & 1u) != 0;
-          near_c = !EXACT && live && !ones_c && (d < 0 ? -d : d) <= a.pmp * (R)1e-9;
+          // a field with a bitmap accumulates WB*W per tap in floating point (budget_interp_mod.F90:262-277) even when
+          // every tap is usable, a field without one the integer WB: next to the threshold (mp = 100) the two can
+          // differ, so the reference's own order and association decide there
+          const R d = (ones_c ? Wall : wo) - a.pmp;
+          near_c = !EXACT && live && (d < 0 ? -d : d) <= a.pmp * (R)1e-9;
           wsel = ones_c ? Wall : wo;
           rsel = ones_c ? rWall : (wo > 0 ? (R)1 / wo : (R)0);
 #pragma unroll
@@ -645,12 +648,14 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
           R acc = 0, wo = 0;
 #pragma unroll
           for (int u = 0; u < U; u++) add2_if<R>((mbp[u >> 2] >> (8 * (u & 3) + f)) & 1u, acc, w[u] * v[u], wo, w[u]);
-          if ((allm >> f) & 1u) {
+          const R dall = Wall - a.pmp;
+          const bool near_all = ((fm >> f) & 1u) != 0 && (dall < 0 ? -dall : dall) <= a.pmp * (R)1e-9;   // bitmap field at the threshold
+          if (((allm >> f) & 1u) && !near_all) {
             good = Wall >= a.pmp;
             og = good ? acc * rWall : (R)0;
           } else {
             const R d = wo - a.pmp;
-            if (live && (d < 0 ? -d : d) <= a.pmp * (R)1e-9) {   // the reference's order and association decide lo
+            if (live && (near_all || (d < 0 ? -d : d) <= a.pmp * (R)1e-9)) {   // the reference's order and association decide lo
               acc = budget_exact_point<R>(a.gi + (size_t)k * mi, a.li + (size_t)k * mi, no, n, true, T.nsamp, T.bn, T.bw, T.wbs, wo);
               good = wo >= a.pmp;
               og = good ? acc / wo : (R)0;

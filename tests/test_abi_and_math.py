@@ -108,3 +108,21 @@ def test_tile_geometry_covers_every_point_once(mode, rowlen, no):
                 if p >= 0:
                     seen[p] += 1
     assert seen.min() == 1 and seen.max() == 1
+
+
+@pytest.mark.parametrize("lsize", ["4", "D", "8"])
+def test_fortran_shim_fits_free_form_line_limit(lsize):
+    """No Fortran compiler exists in the image, so the shim cannot be compiled here; what can be checked is that no
+    statement line exceeds the 132-column free-form limit once cpp has expanded the kind macros (gfortran's default),
+    and that every bind(c) name the shim refers to is exported by the library."""
+    src = os.path.join(ROOT, "fortran", "ip_mod.F90")
+    r = subprocess.run(["cpp", "-P", "-traditional-cpp", f"-DLSIZE={lsize}", src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    code = [ln for ln in r.stdout.splitlines() if ln.strip() and not ln.lstrip().startswith("!")]
+    longest = max(code, key=len)
+    assert len(longest) <= 132, (len(longest), longest)
+    lib = C.CDLL(pkg.PRODUCT_SO)
+    names = set(n for n in re.findall(r"name\s*=\s*'([a-z0-9_]+)'", r.stdout) if re.search(r"_[4d8]$", n))   # imported C symbols
+    assert len(names) >= 10, names
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing

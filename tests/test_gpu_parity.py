@@ -81,6 +81,7 @@ CASES = [
     (2, {}, "127", 4), (2, {1: 4}, "218", 3), (2, {}, "203", 2), (2, {}, "3", 2),
     (3, {}, "203", 3), (3, {}, "218", 3), (3, {1: 1, 2: 1, 3: 1, 4: 40}, "212", 2), (3, {1: 2, 2: -2, 5: 30}, "218", 2),
     (3, {20: 3}, "212", 3), (3, {}, "3", 2),
+    (3, {1: 2, 2: 1, 3: 1, 4: 1, 5: 100}, "218", 4), (3, {1: 1, 2: 1, 3: 1, 4: 100}, "212", 3),   # mp = 100: lo decided at the threshold
     (6, {}, "212", 3), (6, {1: 1, 2: 2, 3: 1, 4: 50}, "218", 2), (6, {}, "3", 2),
 ]
 
@@ -174,7 +175,8 @@ GT_CASES = [(0, {}, "218", 19, "same"), (0, {}, "218", 24, "blocks"), (0, {1: 75
             (2, {}, "218", 19, "each"), (2, {}, "203", 13, "mixed"), (2, {}, "212", 16, "none"),
             (1, {}, "218", 19, "none"), (1, {1: 1}, "8", 17, "mixed"), (1, {}, "203", 16, "none"), (1, {}, "212", 24, "same"),
             (3, {}, "218", 19, "same"), (3, {}, "218", 24, "blocks"), (3, {}, "212", 17, "none"), (3, {}, "203", 16, "each"),
-            (3, {}, "218", 18, "mixed"), (3, {1: 1, 2: 1, 3: 1, 4: 40}, "212", 16, "same"), (3, {}, "3", 16, "same")]
+            (3, {}, "218", 18, "mixed"), (3, {1: 1, 2: 1, 3: 1, 4: 40}, "212", 16, "same"), (3, {}, "3", 16, "same"),
+            (3, {1: 2, 2: 1, 3: 1, 4: 1, 5: 100}, "218", 17, "same"), (3, {1: 2, 2: 1, 3: 1, 4: 1, 5: 100}, "218", 16, "mixed")]
 
 
 def _gt_case(kind, ip, over, grid, km, pat):
