@@ -86,6 +86,22 @@ def synth_mask_np(k, im=1440, jm=721):
     return (h < 7).astype(np.uint8).reshape(-1)
 
 
+def survey_plan_bytes_per_point(wl, R_bytes):
+    """Plan bytes per output point as SURVEY.md section 8 (a4)/(d) counts them: bilinear NXY(2,2)+WXY(2,2) = 16 + 4 R
+    (32 B in the _4 kind), + CXY/SXY/CROT/SROT for vectors, bicubic 16 taps + class byte, neighbor index + x,y; budget: the
+    collapsed variant this library applies (9 positions + 9 weights + the weight sum; the survey asks to report the variant)."""
+    ip, vec = wl["ip"], wl["vector"]
+    if ip == 0:
+        return 16 + 4 * R_bytes + (10 * R_bytes if vec else 0)
+    if ip == 1:
+        return 64 + 16 * R_bytes + 1 + (34 * R_bytes if vec else 0)
+    if ip == 2:
+        return 4 + 2 * R_bytes
+    if ip == 3:
+        return 9 * (4 + R_bytes) + R_bytes
+    return 25 * 4
+
+
 def algorithmic_bytes(wl, R_bytes, no, touched, plan_bytes_per_pt, km):
     """Compulsory HBM traffic per output point x field: each output element written once, each touched source
     element read once, the plan read once per call."""
@@ -96,23 +112,55 @@ def algorithmic_bytes(wl, R_bytes, no, touched, plan_bytes_per_pt, km):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock, power and throttle reasons while the GPU is under load (B200_PROFILING.md recipe), sampled every few
+    milliseconds through NVML from a side thread — started BEFORE the warm-up steps and stopped after the timed region, so
+    that even a 100 ms timed region sees tens of samples; nvidia-smi is the fallback when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.stop, self.t = index, [], threading.Event(), None
+        self.timed = None       # (t0, t1) of the timed region, perf_counter
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES when it holds plain indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = index
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                phys = int(vis.split(",")[index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+        pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        bits = [getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8), getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20), getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)]
+        return [time.perf_counter(), float(sm), float(mx), float(pw)] + [bool(r & b) for b in bits]
+
+    def _sample_smi(self):
+        o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                           capture_output=True, text=True, timeout=5).stdout.strip()
+        x = [v.strip() for v in o.split(",")]
+        return [time.perf_counter(), float(x[0]), float(x[1]), float(x[2])] + [v.lower().startswith("active") for v in x[3:7]]
 
     def _run(self):
         while not self.stop.is_set():
             try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([x.strip() for x in o.split(",")])
+                self.rows.append(self._sample_nvml() if self.nvml else self._sample_smi())
             except Exception:
                 pass
-            self.stop.wait(0.05)
+            self.stop.wait(0.002 if self.nvml else 0.05)
 
     def __enter__(self):
         self.t = threading.Thread(target=self._run, daemon=True)
@@ -126,12 +174,21 @@ class ClockSampler:
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        load = self.rows
+        if self.timed:
+            inside = [r for r in self.rows if self.timed[0] <= r[0] <= self.timed[1]]
+        else:
+            inside = []
+        sm = sorted(r[1] for r in load)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for c, n in enumerate(names) if any(len(r) > 3 + c and r[3 + c].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
-                "power_w_max": max((float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()), default=None),
-                "samples": len(self.rows), "reasons": reasons}
+        reasons = [n for c, n in enumerate(names) if any(r[4 + c] for r in load)]
+        out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": load[0][2], "power_w_max": max(r[3] for r in load), "samples": len(load),
+               "samples_in_timed_region": len(inside), "window": "warm-up + timed region", "source": "nvml" if self.nvml else "nvidia-smi",
+               "reasons": reasons}
+        if inside:
+            smi = sorted(r[1] for r in inside)
+            out["sm_mhz_timed_region"] = smi[len(smi) // 2]
+        return out
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -213,7 +270,7 @@ def run_reference(args, wl):
     c = cpu_arm(wl, target_s=max(2.0, 90.0 / max(args.steps + args.warmup, 1)), steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": c["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": c["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": c["seconds"] * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32" if wl["kind"] == "4" else "f64", "data": "synthetic",
         "config": {"workload": wl["desc"], "sample_km": c["km"], "note": "CPU arm: oracle port of the reference's OpenMP path "
                    "(no Fortran compiler in this image, so the reference itself cannot be built); runs on rank 0 only"},
@@ -269,12 +326,15 @@ def run_gpu(args, wl):
     gin, gout = G[wl["src"]], G[wl["dst"]]
     im, jm = gin[2][7], gin[2][8]
     mi, mo = im * jm, gout[2][7] * gout[2][8]
-    km = args.km or wl["km"]
+    km_total = args.km or wl["km"]
+    strong = args.scaling == "strong"
+    # weak: every rank owns km fields; strong: the km fields of the workload are split over the ranks (rank r owns a contiguous slice)
+    km = (km_total * (rank + 1) // world - km_total * rank // world) if strong else km_total
     vec, ip = wl["vector"], wl["ip"]
     opt = ipopt_for(ip)
 
     # ---- synthetic inputs, generated on the device (same formula as synth_field_np) -----------------------
-    k_global0 = rank * km   # every rank owns its own slice of the (N*km)-field batch
+    k_global0 = (km_total * rank // world) if strong else rank * km   # every rank owns its own slice of the field batch
     ii = torch.arange(im, device=dev, dtype=torch.float64)[None, None, :]
     jj = torch.arange(jm, device=dev, dtype=torch.float64)[None, :, None]
     gi = torch.empty((km, mi), dtype=tR, device=dev)
@@ -326,6 +386,8 @@ def run_gpu(args, wl):
             raise RuntimeError(f"ipolates returned iret={int(sc['iret'][0])}")
 
     pm, am, hit = C.c_double(0), C.c_double(0), C.c_int(0)
+    clk = ClockSampler(local)
+    clk.__enter__()                                   # samples from here (plan build, warm-up) to the end of the timed region
     step()                                            # first call builds the plan (reported separately)
     L.ipgpu_last_timing(C.byref(pm), C.byref(am), C.byref(hit))
     plan_build_ms = pm.value
@@ -347,14 +409,16 @@ def run_gpu(args, wl):
     launches0 = L.ipgpu_launch_count()
     apply_ms = []
     barrier()
-    with ClockSampler(local) as clk:
-        e0.record()
-        for _ in range(args.steps):
-            step()
-            L.ipgpu_last_timing(C.byref(pm), C.byref(am), C.byref(hit))
-            apply_ms.append(am.value)
-        e1.record()
-        barrier()
+    t_begin = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+        L.ipgpu_last_timing(C.byref(pm), C.byref(am), C.byref(hit))
+        apply_ms.append(am.value)
+    e1.record()
+    barrier()
+    clk.timed = (t_begin, time.perf_counter())
+    clk.__exit__()
     ms = e0.elapsed_time(e1)
     launches = L.ipgpu_launch_count() - launches0
     t = torch.tensor([ms, float(launches)], dtype=torch.float64, device=dev)
@@ -366,18 +430,19 @@ def run_gpu(args, wl):
     else:
         launches = float(t[1])
     ms_per_step = ms / args.steps
-    value = world * no * km / (ms_per_step * 1e-3)
+    units_all = no * (km_total if strong else world * km)       # point x fields all ranks processed per step
+    value = units_all / (ms_per_step * 1e-3)
 
     # ---- roofline of the dominant (apply) kernel ------------------------------------------------------
     plan_bytes = L.ipgpu_plan_bytes()
     touched = args_touched(wl)
     Rb = np.dtype(R).itemsize
-    plan_pp = plan_bytes / max(no, 1)
-    if wl["ip"] == 3 and kind != "4":
-        # budget, binary64 kinds: the apply kernel reads the collapsed taps (9 positions + 9 weights + the weight sum per
-        # point, csrc/ipb_budget.cuh), not the 1200 B/point sub-sample plan it was derived from
-        plan_pp = 9 * (4 + Rb) + Rb
-    bpu = algorithmic_bytes(wl, Rb, no, touched, plan_pp, km)
+    # algorithmic bytes per unit exactly as SURVEY.md section 8(d) defines them: output written once, touched source read
+    # once, the reference's plan read once per call.  (The plan this library keeps in HBM is larger — staging tables,
+    # packed weight records — and mostly not read by the apply kernel; that variant is reported beside it.)
+    plan_pp = survey_plan_bytes_per_point(wl, Rb)
+    bpu = algorithmic_bytes(wl, Rb, no, touched, plan_pp, max(km, 1))
+    bpu_repo = algorithmic_bytes(wl, Rb, no, touched, plan_bytes / max(no, 1), max(km, 1))
     k_ms = sum(apply_ms) / len(apply_ms)
     peaks = {}
     try:
@@ -388,7 +453,7 @@ def run_gpu(args, wl):
     achieved = bpu * no * km / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": load_traffic(args.workload) if not (args.km or args.kind or args.mask >= 0) else None,   # measured at the workload's own size only
-                "kernel_ms": k_ms, "bytes_per_unit": bpu, "units_per_launch": no * km,
+                "kernel_ms": k_ms, "bytes_per_unit": bpu, "bytes_per_unit_with_this_librarys_whole_plan": bpu_repo, "units_per_launch": no * km,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, burst)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "frac_of_nominal_8TBs": achieved / 8000.0}
 
@@ -439,37 +504,65 @@ def run_gpu(args, wl):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f32" if kind == "4" else "f64", "data": "synthetic",
-            "config": {"workload": wl["desc"], "km_per_gpu": km, "no": no, "mi": mi, "ip": ip, "kind": "_" + kind,
+            "config": {"workload": wl["desc"], "km_per_gpu": km, "km_total": km_total if strong else world * km, "no": no, "mi": mi, "ip": ip, "kind": "_" + kind,
                        "cache_defeat": "inputs+outputs per step (%.1f GB) exceed L2 (126 MB)" % ((gi.numel() * (2 if vec else 1) * Rb + go.numel() * (2 if vec else 1) * Rb + lo.numel()) / 1e9),
                        "plan": "cached (built once: %.2f ms in a cold process, %.2f ms warm, %.1f MB in HBM); sharding: km fields per rank, no collective" % (plan_build_ms, plan_rebuild_ms, plan_bytes / 1e6)},
+            "plan_build": plan_build_report(args.workload, plan_rebuild_ms, no),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),
             "plan_build_ms": plan_build_ms, "plan_rebuild_ms_warm": plan_rebuild_ms,
         }
         if plan_bcast_ms is not None:
             line["plan_nccl_broadcast_ms_same_bytes"] = plan_bcast_ms
-        if world == 1 and args.workload == "bilinear" and not args.no_secondary:
-            line["secondary"] = secondary_budget()
+        if world == 1 and args.workload == "bilinear" and not args.no_secondary and not args.km:
+            line["secondary"] = secondary_budget(args)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def secondary_budget():
+def secondary_budget(args):
     """BASELINE's metric names two workloads ("bilinear+budget"); the line above is the bilinear one.  The budget
-    configuration (ip=3, _d, land-mask bitmap, km=256) is measured right after it in a child process — same code path
-    as `bench.py --workload budget` — and its device-resident numbers are attached under "secondary"."""
+    configuration (ip=3, _d, land-mask bitmap, km=256) is measured right after it in a child process — the same code path
+    as `bench.py --workload budget`, with its own CPU spot check and its own end-to-end number — and attached under
+    "secondary" as a complete line of its own."""
     try:
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", "budget", "--steps", "10", "--warmup", "3",
-                            "--no-cpu", "--no-e2e", "--no-secondary"], capture_output=True, text=True, timeout=300)
+        cmd = [sys.executable, os.path.abspath(__file__), "--workload", "budget", "--steps", "10", "--warmup", "3", "--no-secondary",
+               "--cpu-seconds", "6"]
+        if args.no_cpu:
+            cmd.append("--no-cpu")
+        if args.no_e2e:
+            cmd.append("--no-e2e")
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=420)
         d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
-        return {"workload": d["config"]["workload"], "value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"],
-                "dtype": d["dtype"], "steps": d["steps"], "warmup": d["warmup"], "roofline": d["roofline"], "gpu_launches": d["gpu_launches"],
-                "plan_build_ms": d["plan_build_ms"], "plan_rebuild_ms_warm": d.get("plan_rebuild_ms_warm")}
+        keep = ("metric", "value", "unit", "ms_per_step", "dtype", "steps", "warmup", "roofline", "cpu_baseline", "e2e", "gpu_launches",
+                "plan_build_ms", "plan_rebuild_ms_warm", "plan_build", "clocks")
+        out = {"workload": d["config"]["workload"]}
+        out.update({k: d.get(k) for k in keep})
+        return out
     except Exception as e:  # the headline line must not depend on it
         return {"error": repr(e)[:200]}
+
+
+# FP64 work of the plan-building kernels, from the committed ncu capture (profiles/plan_fp64.json: thread-level DFMA / DMUL /
+# DADD counts of one plan build of the workload).  north_star asks for the plan build "against FP64 peak".
+FP64_PEAK_TFLOPS = 37.2   # 148 SMs x 64 FP64 lanes x 2 flop x 1.965 GHz (B200 nominal: 40 TFLOP/s)
+
+
+def plan_build_report(workload, rebuild_ms, no):
+    rep = {"ms_warm": rebuild_ms, "points_per_s": (no / (rebuild_ms * 1e-3)) if rebuild_ms else None, "fp64_peak_tflops": FP64_PEAK_TFLOPS}
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "plan_fp64.json"))).get(workload)
+        if d:
+            flops = 2 * d["dfma"] + d["dmul"] + d["dadd"]
+            rep.update({"fp64_flop": flops, "fp64_kernel_ms": d["kernel_ms"], "fp64_tflops": flops / (d["kernel_ms"] * 1e-3) / 1e12,
+                        "fp64_frac_of_peak": flops / (d["kernel_ms"] * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
+                        "source": "profiles/plan_fp64.json (ncu sass op counts and durations of the plan kernels, one build)"})
+    except Exception:
+        pass
+    return rep
 
 
 def args_touched(wl):
@@ -545,7 +638,7 @@ def run_e2e(args, wl, lib, L, torch, dist, dev, world, gin, gout, mi, mo, km, no
 
     f(*a)   # warm-up (plan is cached already; staging buffers get allocated)
     assert sc["iret"][0] == 0, sc["iret"][0]
-    nstep = max(1, min(args.steps, 3))
+    nstep = max(1, min(args.steps, 5))
     sync()
     t0 = time.perf_counter()
     for _ in range(nstep):
@@ -562,9 +655,18 @@ def run_e2e(args, wl, lib, L, torch, dist, dev, world, gin, gout, mi, mo, km, no
     ok = bool(np.array_equal(h_lo[0], lo[0].cpu().numpy())) and bool(np.array_equal(h_go[0].view(np.uint8), go[0].cpu().numpy().view(np.uint8)))
     for p_ in bufs:
         L.ipgpu_host_free(C.c_void_p(p_))
+    # the ceiling of this rank's host link, measured in this process with the same pinned allocator (one large copy per
+    # direction, then both at once); the call is D2H dominated, so its floor is d2h bytes / d2h rate
+    lp = [C.c_double(0), C.c_double(0), C.c_double(0)]
+    L.ipgpu_link_probe.argtypes = [C.c_longlong, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.ipgpu_link_probe(C.c_longlong(256 << 20), C.byref(lp[0]), C.byref(lp[1]), C.byref(lp[2]))
+    d2h_b, h2d_b = int(d2h.value) + 2 * mo * Rb + kme * 4, int(h2d.value) + kme * 4
+    floor_ms = max(d2h_b / max(lp[1].value, 1e-9), h2d_b / max(lp[0].value, 1e-9)) / 1e6
     # bytes of the whole job (every rank moves the same amount over its own PCIe link)
-    return {"value": world * no * kme / dt, "unit": UNIT, "h2d_bytes_per_step": world * (int(h2d.value) + kme * 4),
-            "d2h_bytes_per_step": world * (int(d2h.value) + 2 * mo * Rb + kme * 4), "ms_per_step": dt * 1e3, "km_per_gpu": kme, "steps": nstep,
+    return {"value": world * no * kme / dt, "unit": UNIT, "h2d_bytes_per_step": world * h2d_b,
+            "d2h_bytes_per_step": world * d2h_b, "ms_per_step": dt * 1e3, "km_per_gpu": kme, "steps": nstep,
+            "pcie_gbs_peak": {"h2d": lp[0].value, "d2h": lp[1].value, "both_directions": lp[2].value, "how": "ipgpu_link_probe, 256 MiB pinned copies"},
+            "link_floor_ms": floor_ms, "frac_of_link_ceiling": floor_ms / (dt * 1e3), "numa_node_of_gpu": int(L.ipgpu_device_numa_node()),
             "api": ("ipolatev_grib2_" if vec else "ipolates_grib2_") + wl["kind"] + " (host pointers, pinned; only the source window the plan references is copied in)",
             "matches_device_path": ok}
 
@@ -583,6 +685,9 @@ def main():
     ap.add_argument("--no-secondary", action="store_true", help="skip the budget configuration attached to the default (bilinear) line")
     ap.add_argument("--chunk-mib", type=int, default=0, help="staging size per in-flight chunk of the host-pointer path (default: the library's, 768)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --km fields per GPU (default; the driver's SCALE run); strong: the workload's km fields split over the GPUs "
+                         "(BASELINE config 5: --workload neighbor|bicubic --km 8192 --scaling strong)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 1)

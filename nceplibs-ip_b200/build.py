@@ -23,7 +23,9 @@ NVCC_FLAGS = [
 
 
 def sources():
-    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
+    root = os.path.dirname(HERE)
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(root, "shims", "ip_shim.c"), os.path.join(root, "include", "iplib.h"),
+                                                                        os.path.join(root, "include", "ipb200.h")]
 
 
 STAMP = os.path.join(OBJ, "libipb200.sha256")
@@ -39,7 +41,7 @@ def source_digest(extra=()):
 
 
 def up_to_date(extra=()):
-    if not (os.path.exists(OUT) and os.path.exists(STAMP)):
+    if not (os.path.exists(OUT) and os.path.exists(STAMP) and all(os.path.exists(os.path.join(HERE, f"libip_{k}.so")) for k in "4d8")):
         return False
     return open(STAMP).read().strip() == source_digest(extra)
 
@@ -68,6 +70,23 @@ def build_library(force=False, verbose=False, extra=()):
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)
+    build_shims(verbose)
     with open(STAMP, "w") as f:
         f.write(source_digest(extra) + "\n")
     return OUT
+
+
+def build_shims(verbose=False):
+    """libip_4.so / libip_d.so / libip_8.so: the reference's unsuffixed C symbols forwarding to libipb200.so (shims/ip_shim.c)."""
+    root = os.path.dirname(HERE)
+    src = os.path.join(root, "shims", "ip_shim.c")
+    outs = []
+    for lsize, sfx in (("4", "4"), ("D", "d"), ("8", "8")):
+        out = os.path.join(HERE, f"libip_{sfx}.so")
+        cmd = ["gcc", "-O2", "-shared", "-fPIC", "-Wall", "-Werror", f"-DLSIZE={lsize}", "-I", os.path.join(root, "include"), src, "-o", out,
+               "-L", HERE, "-lipb200", "-Wl,-rpath,$ORIGIN"]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+        outs.append(out)
+    return outs

@@ -126,3 +126,20 @@ def test_fortran_shim_fits_free_form_line_limit(lsize):
     assert len(names) >= 10, names
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
+
+
+def test_kind_shims_export_the_reference_symbols():
+    """libip_4 / libip_d / libip_8 (shims/ip_shim.c): the unsuffixed names the reference's libraries export, for C callers."""
+    pkg.build_library()
+    here = os.path.dirname(pkg.PRODUCT_SO)
+    want = ["gdswzd", "gdswzd_grib1"] + [f"ipolate{sv}_grib{g}{sf}" for sv in "sv" for g in "12" for sf in ("", "_single_field")]
+    for k in "4d8":
+        r = subprocess.run(["nm", "-D", "--defined-only", os.path.join(here, f"libip_{k}.so")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        have = set(line.split()[-1] for line in r.stdout.splitlines() if " T " in line)
+        assert set(want) <= have, (k, sorted(set(want) - have))
+    src = '#include "iplib.h"\nint main(void){return 0;}\n'
+    for ls in ("4", "D", "8"):
+        r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", f"-DLSIZE={ls}", "-I", os.path.join(ROOT, "include"), "-x", "c", "-"],
+                           input=src, text=True, capture_output=True)
+        assert r.returncode == 0, r.stderr

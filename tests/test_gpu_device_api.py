@@ -297,3 +297,22 @@ def test_host_call_sharded_over_devices():
                       np.resize(v, (km, ic.npts_of(ic.g2_input("4", True)))))
     for k in ("uo", "vo", "lo", "ibo", "crot", "srot"):
         assert np.array_equal(v1[k], vm[k]), k
+
+
+@pytest.mark.parametrize("lsize,sfx", [("4", "4"), ("D", "d"), ("8", "8")])
+def test_c_caller_links_the_kind_shims(lsize, sfx, tmp_path):
+    """A C program written against the reference's C interface (unsuffixed gdswzd / gdswzd_grib1 / ipolates_grib2, include/iplib.h)
+    links libip_<kind>.so and passes the checks of tests/tst_gdswzd_grib2.c / tst_gdswzd_grib1.c on the GPU."""
+    import importlib
+    import os
+    import subprocess
+    pkg = importlib.import_module("nceplibs-ip_b200")
+    pkg.build_library()
+    here = os.path.dirname(pkg.PRODUCT_SO)
+    root = os.path.dirname(here)
+    exe = str(tmp_path / f"tst_gdswzd_{sfx}")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", f"-DLSIZE={lsize}", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "native", "tst_gdswzd_c.c"),
+                           "-o", exe, "-L", here, f"-lip_{sfx}", "-lipb200", "-lm", f"-Wl,-rpath,{here}"])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr
