@@ -421,7 +421,7 @@ inline PFN_tmap_encode tmap_encoder() {
   return fn;
 }
 
-template <class R> bool launch_bilinear_box(const Plan<R>& P, const FieldArgs<R>& a, cudaStream_t st) {
+template <class R, int F> bool launch_bilinear_box_f(const Plan<R>& P, const FieldArgs<R>& a, cudaStream_t st) {
   PFN_tmap_encode enc = tmap_encoder();
   if (!enc) return false;
   const GridP<R>& gi = P.gin.p;
@@ -429,7 +429,7 @@ template <class R> bool launch_bilinear_box(const Plan<R>& P, const FieldArgs<R>
   static const int kpt_env = getenv("IPB_BOX_KPT") ? atoi(getenv("IPB_BOX_KPT")) : 32;
   static const int warps_env = getenv("IPB_BOX_WARPS") ? atoi(getenv("IPB_BOX_WARPS")) : 4;
   static const int minb_env = getenv("IPB_BOX_MINB") ? atoi(getenv("IPB_BOX_MINB")) : 6;
-  constexpr int NR = 4, F = 8;
+  constexpr int NR = 4;
   int unit = (align_env >= 16 && align_env <= 128 ? align_env : 128) / (int)sizeof(R);       // elements; a power of two >= 4 (lo words)
   if (unit < 4) unit = 4;
   const int WARPS = warps_env == 8 ? 8 : 4;
@@ -480,13 +480,18 @@ template <class R> bool launch_bilinear_box(const Plan<R>& P, const FieldArgs<R>
     if (!once[dv_]) { IPB_CUDA(cudaFuncSetAttribute(k_bilinear_box<R, NR, F, TH, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); once[dv_] = true; } \
     k_bilinear_box<R, NR, F, TH, MB><<<grid, TH, SM, st>>>(tm4, tm3, a, P.nxy, P.bxy, P.wq, P.ws2, G, kpt);                  \
   }
-  if (WARPS == 8) { if (minb_env >= 3) IPB_BOX_LAUNCH(256, 3) else IPB_BOX_LAUNCH(256, 2) }
+  if (WARPS == 8) IPB_BOX_LAUNCH(256, 3)
   else if (minb_env >= 6) IPB_BOX_LAUNCH(128, 6)
   else if (minb_env == 5) IPB_BOX_LAUNCH(128, 5)
   else IPB_BOX_LAUNCH(128, 4)
 #undef IPB_BOX_LAUNCH
   g_launches++;
   return true;
+}
+
+template <class R> bool launch_bilinear_box(const Plan<R>& P, const FieldArgs<R>& a, cudaStream_t st) {
+  // fields staged per pass: 8 (measured at km = 1024: 4 -> 2.18 ms, 8 -> 2.12 ms, 16 -> 2.24 ms; profiles/README.md)
+  return launch_bilinear_box_f<R, 8>(P, a, st);
 }
 
 }  // namespace ipb
