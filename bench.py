@@ -636,6 +636,10 @@ def run_e2e(args, wl, lib, L, torch, dist, dev, world, gin, gout, mi, mo, km, no
             dist.barrier()
         torch.cuda.synchronize()
 
+    ndev_lib = 1
+    if getattr(args, "devices", 1) > 1 and world == 1:
+        # one process, one host-pointer call, the field batch sharded over n GPUs inside the library (ipgpu_set_devices)
+        ndev_lib = int(L.ipgpu_set_devices(C.c_int(args.devices)))
     f(*a)   # warm-up (plan is cached already; staging buffers get allocated)
     assert sc["iret"][0] == 0, sc["iret"][0]
     nstep = max(1, min(args.steps, 5))
@@ -653,6 +657,9 @@ def run_e2e(args, wl, lib, L, torch, dist, dev, world, gin, gout, mi, mo, km, no
     L.ipgpu_last_transfer(C.byref(h2d), C.byref(d2h))
     # result read-back is part of the call: go/lo are host arrays when it returns
     ok = bool(np.array_equal(h_lo[0], lo[0].cpu().numpy())) and bool(np.array_equal(h_go[0].view(np.uint8), go[0].cpu().numpy().view(np.uint8)))
+    ok = ok and bool(np.array_equal(h_go[kme - 1].view(np.uint8), go[kme - 1].cpu().numpy().view(np.uint8)))   # last field: another device when sharded
+    if ndev_lib > 1:
+        L.ipgpu_set_devices(C.c_int(1))
     for p_ in bufs:
         L.ipgpu_host_free(C.c_void_p(p_))
     # the ceiling of this rank's host link, measured in this process with the same pinned allocator (one large copy per
@@ -667,6 +674,7 @@ def run_e2e(args, wl, lib, L, torch, dist, dev, world, gin, gout, mi, mo, km, no
             "d2h_bytes_per_step": world * d2h_b, "ms_per_step": dt * 1e3, "km_per_gpu": kme, "steps": nstep,
             "pcie_gbs_peak": {"h2d": lp[0].value, "d2h": lp[1].value, "both_directions": lp[2].value, "how": "ipgpu_link_probe, 256 MiB pinned copies"},
             "link_floor_ms": floor_ms, "frac_of_link_ceiling": floor_ms / (dt * 1e3), "numa_node_of_gpu": int(L.ipgpu_device_numa_node()),
+            "devices_in_library": ndev_lib,
             "api": ("ipolatev_grib2_" if vec else "ipolates_grib2_") + wl["kind"] + " (host pointers, pinned; only the source window the plan references is copied in)",
             "matches_device_path": ok}
 
@@ -685,6 +693,7 @@ def main():
     ap.add_argument("--no-secondary", action="store_true", help="skip the budget configuration attached to the default (bilinear) line")
     ap.add_argument("--chunk-mib", type=int, default=0, help="staging size per in-flight chunk of the host-pointer path (default: the library's, 768)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--devices", type=int, default=1, help="single process: shard the host-pointer (e2e) call over this many GPUs inside the library")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --km fields per GPU (default; the driver's SCALE run); strong: the workload's km fields split over the GPUs "
                          "(BASELINE config 5: --workload neighbor|bicubic --km 8192 --scaling strong)")
