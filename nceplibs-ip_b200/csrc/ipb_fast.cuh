@@ -223,7 +223,7 @@ k_neighbor_lane(FieldArgs<R> a, const int* __restrict__ nxy, int kpb, int rowlen
 // mapping, and the usable bits travel to the storing lanes by shuffle.
 template <class R, bool MASKED>
 __global__ void __launch_bounds__(128)
-k_neighbor_patch(FieldArgs<R> a, const int* __restrict__ nxy, int kpb, int rowlen, int ntx, int npatch) {
+k_neighbor_patch(FieldArgs<R> a, const int* __restrict__ nxy, int kpb, int rowlen, int ntx, int npatch, int amask, int period, int base_e) {
   constexpr int FB = 4, PITCH = 40;
   __shared__ R tile_all[4][2][FB][4 * PITCH];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -231,6 +231,13 @@ k_neighbor_patch(FieldArgs<R> a, const int* __restrict__ nxy, int kpb, int rowle
   if (patch >= npatch) return;
   R (*tile)[FB][4 * PITCH] = tile_all[w];
   const int col0 = (patch % ntx) * 32, row0 = (patch / ntx) * 4;
+  // Fields with the same element phase of go(:,k) form a class (k = cls + period * j); the 32-point run of every output
+  // row is shifted per class and row so that it starts on a 128-byte line of the caller's go array and on a 32-byte
+  // sector of lo (stores alone, tools/wr_bench2.cu: runs that straddle lines cost 2-3x).  amask = 0: no classes.
+  const int nslice = gridDim.y / period;
+  const int cls = blockIdx.y / nslice, slice = blockIdx.y % nslice;
+  const int phase = (base_e + (int)(((long long)cls * a.mo) & amask)) & amask;
+  auto shift_of = [&](int row) { return (int)(((long long)phase + (long long)row * rowlen) & amask); };
   int pg[4];                   // gather points: 0-based source position, -1 = none
   long long ns[4];             // store points: output index, -1 = outside the grid
   u8 oks[4];
@@ -242,12 +249,12 @@ k_neighbor_patch(FieldArgs<R> a, const int* __restrict__ nxy, int kpb, int rowle
     int vg[4], vs[4];
 #pragma unroll
     for (int s = 0; s < 4; s++) {
-      const int gc = col0 + 8 * s + (lane & 7), gr = row0 + (lane >> 3);
+      const int gr = row0 + (lane >> 3), gc = col0 - shift_of(gr) + 8 * s + (lane & 7);
       ng[s] = (long long)gr * rowlen + gc;
-      if (!(gc < rowlen && ng[s] < a.no)) ng[s] = -1;
-      const int sc = col0 + lane, sr = row0 + s;
+      if (!(gc >= 0 && gc < rowlen && ng[s] < a.no)) ng[s] = -1;
+      const int sr = row0 + s, sc = col0 - shift_of(sr) + lane;
       const long long n = (long long)sr * rowlen + sc;
-      ns[s] = (sc < rowlen && n < a.no) ? n : -1;
+      ns[s] = (sc >= 0 && sc < rowlen && n < a.no) ? n : -1;
     }
 #pragma unroll
     for (int s = 0; s < 4; s++) { vg[s] = __ldg(nxy + (ng[s] >= 0 ? ng[s] : 0)); vs[s] = __ldg(nxy + (ns[s] >= 0 ? ns[s] : 0)); }
@@ -258,23 +265,25 @@ k_neighbor_patch(FieldArgs<R> a, const int* __restrict__ nxy, int kpb, int rowle
       anybad = anybad || (ns[s] >= 0 && !oks[s]);
     }
   }
-  const int k0 = blockIdx.y * kpb, k1 = min(k0 + kpb, a.kc);
+  // fields of this block: kf(j) = cls + period * j, j in [k0, k1)   (period = 1, cls = 0 without classes)
+  const int k0 = slice * kpb, k1 = min(k0 + kpb, (a.kc - cls + period - 1) / period);
   if (k0 >= k1) return;
-  const R* __restrict__ g = a.gi + (size_t)k0 * a.mi;
-  const u8* __restrict__ l = MASKED ? a.li + (size_t)k0 * a.mi : nullptr;
-  R* go = a.go + (size_t)k0 * a.mo;
-  u8* lo = a.lo + (size_t)k0 * a.mo;
+  const size_t gstep = (size_t)period * a.mi, ostep = (size_t)period * a.mo;
+  const R* __restrict__ g = a.gi + (size_t)(cls + period * k0) * a.mi;
+  const u8* __restrict__ l = MASKED ? a.li + (size_t)(cls + period * k0) * a.mi : nullptr;
+  R* go = a.go + (size_t)(cls + period * k0) * a.mo;
+  u8* lo = a.lo + (size_t)(cls + period * k0) * a.mo;
   const int wslot = (lane >> 3) * PITCH + (lane & 7);
   // values (and, MASKED, bitmap bytes: 1 where the field has none) of one round at this lane's gather points
   auto gather = [&](R (&v)[FB][4], u8 (&m)[FB][4], int k) {
 #pragma unroll
     for (int f = 0; f < FB; f++) {
-      const bool mk = MASKED && k + f < k1 && a.ibi[k + f] != 0;
+      const bool mk = MASKED && k + f < k1 && a.ibi[cls + period * (k + f)] != 0;
 #pragma unroll
       for (int s = 0; s < 4; s++) {
         const bool on = pg[s] >= 0 && k + f < k1;
-        v[f][s] = on ? __ldg(g + (size_t)f * a.mi + pg[s]) : (R)0;
-        m[f][s] = (MASKED && mk && on) ? __ldg(l + (size_t)f * a.mi + pg[s]) : (u8)1;
+        v[f][s] = on ? __ldg(g + (size_t)f * gstep + pg[s]) : (R)0;
+        m[f][s] = (MASKED && mk && on) ? __ldg(l + (size_t)f * gstep + pg[s]) : (u8)1;
       }
     }
   };
@@ -293,8 +302,8 @@ k_neighbor_patch(FieldArgs<R> a, const int* __restrict__ nxy, int kpb, int rowle
         tile[buf][f][wslot + 8 * s] = (!MASKED || ok) ? v[f][s] : (R)0;
       }
     }
-    g += (size_t)FB * a.mi;
-    if (MASKED) l += (size_t)FB * a.mi;
+    g += (size_t)FB * gstep;
+    if (MASKED) l += (size_t)FB * gstep;
     if (k + FB < k1) gather(vn, mn, k + FB);     // in flight while this round is stored
     __syncwarp();
     const int nf = min(FB, k1 - k);
@@ -310,15 +319,15 @@ k_neighbor_patch(FieldArgs<R> a, const int* __restrict__ nxy, int kpb, int rowle
           if (ns[r] >= 0) {
             // store point (row r, column lane) is sub-patch point s = lane/8 of lane r*8 + lane%8
             const u8 ok = MASKED ? (u8)((gbs[r] >> (4 * f + (lane >> 3))) & 1u) : oks[r];
-            __stcs(go + (size_t)f * a.mo + ns[r], tile[buf][f][r * PITCH + lane]);
-            __stcs(lo + (size_t)f * a.mo + ns[r], ok);
+            __stcs(go + (size_t)f * ostep + ns[r], tile[buf][f][r * PITCH + lane]);
+            __stcs(lo + (size_t)f * ostep + ns[r], ok);
             bad = bad || !ok;
           }
         }
-        if (MASKED && bad) mark_bad(a.flag, k + f);
+        if (MASKED && bad) mark_bad(a.flag, cls + period * (k + f));
       }
     }
-    go += (size_t)FB * a.mo; lo += (size_t)FB * a.mo;
+    go += (size_t)FB * ostep; lo += (size_t)FB * ostep;
 #pragma unroll
     for (int f = 0; f < FB; f++) {
 #pragma unroll
@@ -326,7 +335,7 @@ k_neighbor_patch(FieldArgs<R> a, const int* __restrict__ nxy, int kpb, int rowle
     }
     buf ^= 1;   // the other buffer was last read two rounds ago, before the previous __syncwarp
   }
-  if (!MASKED && anybad) for (int k = k0; k < k1; k++) mark_bad(a.flag, k);
+  if (!MASKED && anybad) for (int k = k0; k < k1; k++) mark_bad(a.flag, cls + period * k);
 }
 
 template <class R> bool fast_neighbor_ok(const Plan<R>& P, const FieldArgs<R>& a) {
@@ -341,12 +350,22 @@ template <class R> void launch_fast_neighbor(const Plan<R>& P, const FieldArgs<R
   if (!no_patch && orow >= 32 && orow < a.no) {
     // few fields per block: the blocks resident together then write neighbouring patches of the same fields
     // (measured: 12 best, profiles/README.md)
-    static const int kpb_env = getenv("IPB_NKPB") ? atoi(getenv("IPB_NKPB")) : 12;
-    const int kpb = std::max(4, std::min(a.kc, kpb_env));
-    const int ntx = nblk(orow, 32), npatch = ntx * nblk(nblk(a.no, orow), 4);
-    dim3 grid(nblk(npatch, 4), nblk(a.kc, kpb));
-    if (a.li) k_neighbor_patch<R, true><<<grid, 128, 0, st>>>(a, P.nxy, kpb, orow, ntx, npatch);
-    else k_neighbor_patch<R, false><<<grid, 128, 0, st>>>(a, P.nxy, kpb, orow, ntx, npatch);
+    static const int kpb_env = getenv("IPB_NKPB") ? atoi(getenv("IPB_NKPB")) : 32;
+    // line-aligned runs: alignment unit = 128 bytes of go (32 / 16 elements); needs go and lo to share their element phase
+    static const int nalign_env = getenv("IPB_NALIGN") ? atoi(getenv("IPB_NALIGN")) : 128;
+    int unit = std::max(1, nalign_env / (int)sizeof(R));
+    const uintptr_t gp = reinterpret_cast<uintptr_t>(a.go), lp = reinterpret_cast<uintptr_t>(a.lo);
+    if (gp % sizeof(R) || ((gp / sizeof(R)) & (unit - 1)) != (lp & (unit - 1)) || (unit & (unit - 1))) unit = 1;
+    int s_ = (int)(a.mo & (unit - 1)), g_ = unit;
+    while (s_) { const int t = g_ % s_; g_ = s_; s_ = t; }
+    const int period = unit / g_;
+    const int per_class = nblk(a.kc, period);
+    const int kpb = std::max(4, std::min(per_class, kpb_env));
+    const int ntx = nblk(orow + unit - 1, 32), npatch = ntx * nblk(nblk(a.no, orow), 4);
+    dim3 grid(nblk(npatch, 4), period * nblk(per_class, kpb));
+    const int base_e = (int)((gp / sizeof(R)) & (unit - 1));
+    if (a.li) k_neighbor_patch<R, true><<<grid, 128, 0, st>>>(a, P.nxy, kpb, orow, ntx, npatch, unit - 1, period, base_e);
+    else k_neighbor_patch<R, false><<<grid, 128, 0, st>>>(a, P.nxy, kpb, orow, ntx, npatch, unit - 1, period, base_e);
     g_launches++;
     return;
   }
