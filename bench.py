@@ -45,6 +45,10 @@ WORKLOADS = {
                      desc="ipolates bilinear, fp32, 0.25deg global 1440x721 -> 3km CONUS Lambert 1799x1059, km=1024"),
     "budget": dict(ip=3, kind="d", km=256, src="S", dst="L", vector=False, mask=True,
                    desc="ipolates budget (ip=3, ipopt=-1) with li bitmap, fp64, 0.25deg global -> 3km CONUS Lambert, km=256"),
+    "budget4": dict(ip=3, kind="4", km=256, src="S", dst="L", vector=False, mask=True,
+                    desc="ipolates budget (ip=3, ipopt=-1) with li bitmap, fp32 (reference accumulation order, 100 taps per point), 0.25deg global -> 3km CONUS Lambert, km=256"),
+    "nbudget": dict(ip=6, kind="4", km=256, src="S", dst="L", vector=False, mask=True,
+                    desc="ipolates neighbor-budget (ip=6, ipopt=-1) with li bitmap, fp32, 0.25deg global -> 3km CONUS Lambert, km=256"),
     "vector": dict(ip=0, kind="4", km=512, src="S", dst="P", vector=True, mask=False,
                    desc="ipolatev bilinear u/v, fp32, 0.25deg global -> NH polar stereographic 512x512, km=512 pairs"),
     "neighbor": dict(ip=2, kind="4", km=1024, src="S", dst="E", vector=False, mask=False,
@@ -97,8 +101,10 @@ def survey_plan_bytes_per_point(wl, R_bytes):
         return 64 + 16 * R_bytes + 1 + (34 * R_bytes if vec else 0)
     if ip == 2:
         return 4 + 2 * R_bytes
-    if ip == 3:
+    if ip == 3 and R_bytes == 8:
         return 9 * (4 + R_bytes) + R_bytes
+    if ip == 3:
+        return 25 * 4 * (4 + R_bytes)   # the _4 kind keeps the reference's order: 25 sub-samples x 4 taps (index + weight)
     return 25 * 4
 
 
