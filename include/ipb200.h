@@ -80,6 +80,23 @@ void gdswzd_grib1_4(
     const int32_t* kgds, int32_t iopt, int32_t npts, float fill,
     float* xpts, float* ypts, float* rlon, float* rlat, int32_t* nret,
     float* crot, float* srot, float* xlon, float* xlat, float* ylon, float* ylat, float* area);
+/* Grid expanders, every argument by reference like the Fortran routines they replace.
+ * ipxwafs (src/ipxwafs.F90:81): thinned WAFS grid (3447 points) <-> full 73 x 73 grid (5329), linear along each row;
+ * ipxwafs2 (src/ipxwafs2.F90:92): the same with bitmaps; ipxwafs3 (src/ipxwafs3.F90:95): nearest neighbour with bitmaps.
+ * idir > 0 expands, < 0 contracts, 0 only checks; iret 1 = the template is not the WAFS grid.
+ * ipxetas (src/ipxetas.F90:90): staggered Eta E grid (scan 68 / 72) <-> filled E grid (scan 64); iret 1 / 2 / 3 as there. */
+void ipxwafs_4(
+    const int32_t* idir, const int32_t* numpts_thin, const int32_t* numpts_full, const int32_t* km, const int32_t* num_opt, int32_t* opt_pts, const int32_t* igdtlen,
+    int32_t* igdtmpl_thin, float* data_thin, int32_t* igdtmpl_full, float* data_full, int32_t* iret);
+void ipxwafs2_4(
+    const int32_t* idir, const int32_t* numpts_thin, const int32_t* numpts_full, const int32_t* km, const int32_t* num_opt, int32_t* opt_pts, const int32_t* igdtlen,
+    int32_t* igdtmpl_thin, float* data_thin, int32_t* ib_thin, ipb_bool* bitmap_thin, int32_t* igdtmpl_full, float* data_full, int32_t* ib_full, ipb_bool* bitmap_full, int32_t* iret);
+void ipxwafs3_4(
+    const int32_t* idir, const int32_t* numpts_thin, const int32_t* numpts_full, const int32_t* km, const int32_t* num_opt, int32_t* opt_pts, const int32_t* igdtlen,
+    int32_t* igdtmpl_thin, float* data_thin, int32_t* ib_thin, ipb_bool* bitmap_thin, int32_t* igdtmpl_full, float* data_full, int32_t* ib_full, ipb_bool* bitmap_full, int32_t* iret);
+void ipxetas_4(
+    const int32_t* idir, const int32_t* igdtnumi, const int32_t* igdtlen, const int32_t* igdtmpli, const int32_t* npts_input, const ipb_bool* bitmap_input, const float* data_input,
+    int32_t* igdtnumo, int32_t* igdtmplo, const int32_t* npts_output, ipb_bool* bitmap_output, float* data_output, int32_t* iret);
 /* Device-resident variants (new): li, gi/ui/vi, lo, go/uo/vo are DEVICE pointers (on the calling
  * thread's current device) and so are rlat, rlon, crot, srot (each may be NULL to skip that output; for station-point
  * outputs they are inputs).  Scalars, ipopt, the grid definition, ibi, ibo, no and iret stay host memory.  Work is queued
@@ -168,6 +185,23 @@ void gdswzd_grib1_d(
     const int32_t* kgds, int32_t iopt, int32_t npts, double fill,
     double* xpts, double* ypts, double* rlon, double* rlat, int32_t* nret,
     double* crot, double* srot, double* xlon, double* xlat, double* ylon, double* ylat, double* area);
+/* Grid expanders, every argument by reference like the Fortran routines they replace.
+ * ipxwafs (src/ipxwafs.F90:81): thinned WAFS grid (3447 points) <-> full 73 x 73 grid (5329), linear along each row;
+ * ipxwafs2 (src/ipxwafs2.F90:92): the same with bitmaps; ipxwafs3 (src/ipxwafs3.F90:95): nearest neighbour with bitmaps.
+ * idir > 0 expands, < 0 contracts, 0 only checks; iret 1 = the template is not the WAFS grid.
+ * ipxetas (src/ipxetas.F90:90): staggered Eta E grid (scan 68 / 72) <-> filled E grid (scan 64); iret 1 / 2 / 3 as there. */
+void ipxwafs_d(
+    const int32_t* idir, const int32_t* numpts_thin, const int32_t* numpts_full, const int32_t* km, const int32_t* num_opt, int32_t* opt_pts, const int32_t* igdtlen,
+    int32_t* igdtmpl_thin, double* data_thin, int32_t* igdtmpl_full, double* data_full, int32_t* iret);
+void ipxwafs2_d(
+    const int32_t* idir, const int32_t* numpts_thin, const int32_t* numpts_full, const int32_t* km, const int32_t* num_opt, int32_t* opt_pts, const int32_t* igdtlen,
+    int32_t* igdtmpl_thin, double* data_thin, int32_t* ib_thin, ipb_bool* bitmap_thin, int32_t* igdtmpl_full, double* data_full, int32_t* ib_full, ipb_bool* bitmap_full, int32_t* iret);
+void ipxwafs3_d(
+    const int32_t* idir, const int32_t* numpts_thin, const int32_t* numpts_full, const int32_t* km, const int32_t* num_opt, int32_t* opt_pts, const int32_t* igdtlen,
+    int32_t* igdtmpl_thin, double* data_thin, int32_t* ib_thin, ipb_bool* bitmap_thin, int32_t* igdtmpl_full, double* data_full, int32_t* ib_full, ipb_bool* bitmap_full, int32_t* iret);
+void ipxetas_d(
+    const int32_t* idir, const int32_t* igdtnumi, const int32_t* igdtlen, const int32_t* igdtmpli, const int32_t* npts_input, const ipb_bool* bitmap_input, const double* data_input,
+    int32_t* igdtnumo, int32_t* igdtmplo, const int32_t* npts_output, ipb_bool* bitmap_output, double* data_output, int32_t* iret);
 /* Device-resident variants (new): li, gi/ui/vi, lo, go/uo/vo are DEVICE pointers (on the calling
  * thread's current device) and so are rlat, rlon, crot, srot (each may be NULL to skip that output; for station-point
  * outputs they are inputs).  Scalars, ipopt, the grid definition, ibi, ibo, no and iret stay host memory.  Work is queued
@@ -256,6 +290,23 @@ void gdswzd_grib1_8(
     const int64_t* kgds, int64_t iopt, int64_t npts, double fill,
     double* xpts, double* ypts, double* rlon, double* rlat, int64_t* nret,
     double* crot, double* srot, double* xlon, double* xlat, double* ylon, double* ylat, double* area);
+/* Grid expanders, every argument by reference like the Fortran routines they replace.
+ * ipxwafs (src/ipxwafs.F90:81): thinned WAFS grid (3447 points) <-> full 73 x 73 grid (5329), linear along each row;
+ * ipxwafs2 (src/ipxwafs2.F90:92): the same with bitmaps; ipxwafs3 (src/ipxwafs3.F90:95): nearest neighbour with bitmaps.
+ * idir > 0 expands, < 0 contracts, 0 only checks; iret 1 = the template is not the WAFS grid.
+ * ipxetas (src/ipxetas.F90:90): staggered Eta E grid (scan 68 / 72) <-> filled E grid (scan 64); iret 1 / 2 / 3 as there. */
+void ipxwafs_8(
+    const int64_t* idir, const int64_t* numpts_thin, const int64_t* numpts_full, const int64_t* km, const int64_t* num_opt, int64_t* opt_pts, const int64_t* igdtlen,
+    int64_t* igdtmpl_thin, double* data_thin, int64_t* igdtmpl_full, double* data_full, int64_t* iret);
+void ipxwafs2_8(
+    const int64_t* idir, const int64_t* numpts_thin, const int64_t* numpts_full, const int64_t* km, const int64_t* num_opt, int64_t* opt_pts, const int64_t* igdtlen,
+    int64_t* igdtmpl_thin, double* data_thin, int64_t* ib_thin, ipb_bool* bitmap_thin, int64_t* igdtmpl_full, double* data_full, int64_t* ib_full, ipb_bool* bitmap_full, int64_t* iret);
+void ipxwafs3_8(
+    const int64_t* idir, const int64_t* numpts_thin, const int64_t* numpts_full, const int64_t* km, const int64_t* num_opt, int64_t* opt_pts, const int64_t* igdtlen,
+    int64_t* igdtmpl_thin, double* data_thin, int64_t* ib_thin, ipb_bool* bitmap_thin, int64_t* igdtmpl_full, double* data_full, int64_t* ib_full, ipb_bool* bitmap_full, int64_t* iret);
+void ipxetas_8(
+    const int64_t* idir, const int64_t* igdtnumi, const int64_t* igdtlen, const int64_t* igdtmpli, const int64_t* npts_input, const ipb_bool* bitmap_input, const double* data_input,
+    int64_t* igdtnumo, int64_t* igdtmplo, const int64_t* npts_output, ipb_bool* bitmap_output, double* data_output, int64_t* iret);
 /* Device-resident variants (new): li, gi/ui/vi, lo, go/uo/vo are DEVICE pointers (on the calling
  * thread's current device) and so are rlat, rlon, crot, srot (each may be NULL to skip that output; for station-point
  * outputs they are inputs).  Scalars, ipopt, the grid definition, ibi, ibo, no and iret stay host memory.  Work is queued

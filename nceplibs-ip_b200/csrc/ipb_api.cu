@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cctype>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 #include <atomic>
@@ -121,6 +122,10 @@ extern template int plan_geometry<double>(PlanHandle*, void*, double*, double*, 
 extern template int plan_apply<float>(PlanHandle*, void*, i64, const i64*, const u8*, const float*, const float*, int*, u8*, float*, float*);
 extern template int plan_apply<double>(PlanHandle*, void*, i64, const i64*, const u8*, const double*, const double*, int*, u8*, double*, double*);
 
+template <class R> void run_xwafs(int, bool, i64, const i64*, i64, i64, i64, i64, const i64*, const R*, const u8*, R*, u8*, i64*);
+extern template void run_xwafs<float>(int, bool, i64, const i64*, i64, i64, i64, i64, const i64*, const float*, const u8*, float*, u8*, i64*);
+extern template void run_xwafs<double>(int, bool, i64, const i64*, i64, i64, i64, i64, const i64*, const double*, const u8*, double*, u8*, i64*);
+
 namespace {
 
 template <class I> std::vector<i64> widen(const I* p, i64 n) {
@@ -188,6 +193,55 @@ void api_plan_apply(PlanHandle* h, void* stream, i64 km, const I* ibi, const u8*
     auto ib = widen(ibi, km);
     const int rc = plan_apply<R>(h, stream, km, ib.data(), li, gi, vi, d_ibo, lo, go, vo);
     *iret = rc ? (I)1 : (I)(h ? h->iret : 1);
+  } catch (cudaError_t e) { *iret = (I)(1000 + (int)e); } catch (...) { *iret = (I)1001; }
+}
+
+
+// ---- grid expanders ---------------------------------------------------------------------
+// rows of the thinned WAFS grid from the equator to the pole (src/ipxwafs.F90:120-126)
+const int kWafsRow[73] = {73, 73, 73, 73, 73, 73, 73, 73, 72, 72, 72, 71, 71, 71, 70, 70, 69, 69, 68, 67, 67, 66, 65, 65, 64,
+                          63, 62, 61, 60, 60, 59, 58, 57, 56, 55, 54, 52, 51, 50, 49, 48, 47, 45, 44, 43, 42, 40, 39, 38, 36,
+                          35, 33, 32, 30, 29, 28, 26, 25, 23, 22, 20, 19, 17, 16, 14, 12, 11, 9,  8,  6,  5,  3,  2};
+template <class R> i64 nint_r(R x) { return (i64)llround((double)x); }   // Fortran NINT: half away from zero
+
+// ipxwafs (variant 1), ipxwafs2 (2), ipxwafs3 (3): template bookkeeping on the host, the field loop on the device
+template <class R, class I>
+void api_xwafs(int variant, const I* idir, const I* nthin, const I* nfull, const I* km, const I* num_opt, I* opt, const I* len, I* tthin, R* dthin,
+               I* ibthin, u8* bthin, I* tfull, R* dfull, I* ibfull, u8* bfull, I* iret) {
+  try {
+    *iret = 0;
+    if (*len != 19 || *nthin != 3447 || *nfull != 5329) { *iret = 1; return; }
+    const i64 dir = *idir;
+    if (dir > 0) {          // thin -> full: the full grid's template follows from the thin one (ipxwafs.F90:135-156)
+      i64 iscale = (i64)tthin[9] * (i64)tthin[10];
+      if (iscale == 0) iscale = 1000000;
+      const i64 idlat = nint_r<R>((R)1.25 * (R)iscale);
+      bool up = *num_opt == 73, down = *num_opt == 73;
+      for (int j = 0; j < 73 && (up || down); j++) { up = up && opt[j] == kWafsRow[j]; down = down && opt[j] == kWafsRow[72 - j]; }
+      if (!(tthin[18] == 64 && tthin[8] == 73 && idlat == (i64)tthin[17] && (up || down))) { *iret = 1; return; }
+      for (int q = 0; q < 19; q++) tfull[q] = tthin[q];
+      tfull[7] = 73;
+      const R rlon1 = (R)tfull[12] / (R)iscale, rlon2 = (R)tfull[15] / (R)iscale;
+      const R hi = ((tfull[18] / 128) % 2) ? (R)-1 : (R)1;
+      const R dlon = hi * (std::fmod(hi * (rlon2 - rlon1) - (R)1 + (R)3600, (R)360) + (R)1) / (R)72;
+      tfull[16] = (I)nint_r<R>(dlon * (R)iscale);
+    } else if (dir < 0) {   // full -> thin (ipxwafs.F90:157-177)
+      i64 iscale = (i64)tfull[9] * (i64)tfull[10];
+      if (iscale == 0) iscale = 1000000;
+      const i64 idl = nint_r<R>((R)1.25 * (R)iscale);
+      if (!(tfull[18] == 64 && tfull[7] == 73 && tfull[8] == 73 && *num_opt == 73 && idl == (i64)tfull[17] && idl == (i64)tfull[16])) { *iret = 1; return; }
+      for (int q = 0; q < 19; q++) tthin[q] = tfull[q];
+      tthin[7] = (I)-1; tthin[16] = (I)-1;
+      for (int j = 0; j < 73; j++) opt[j] = (I)(tthin[11] == 0 ? kWafsRow[j] : kWafsRow[72 - j]);
+    }
+    if (dir != 1 && dir != -1) return;
+    const bool expand = dir == 1;
+    auto o = widen(opt, 73);
+    std::vector<i64> ibin((size_t)std::max<i64>(*km, 1), 0), ibout((size_t)std::max<i64>(*km, 1), 0);
+    if (variant != 1) for (i64 k = 0; k < *km; k++) ibin[k] = expand ? ibthin[k] : ibfull[k];
+    run_xwafs<R>(variant, expand, *km, o.data(), tfull[8], tfull[7], *nthin, *nfull, ibin.data(), expand ? dthin : dfull, expand ? bthin : bfull,
+                 expand ? dfull : dthin, expand ? bfull : bthin, ibout.data());
+    if (variant != 1) for (i64 k = 0; k < *km; k++) (expand ? ibfull : ibthin)[k] = (I)ibout[k];
   } catch (cudaError_t e) { *iret = (I)(1000 + (int)e); } catch (...) { *iret = (I)1001; }
 }
 
@@ -297,6 +351,59 @@ std::vector<HostMap> g_host_maps;
   void ipgpu_plan_apply_##SFX(void* plan, void* stream, const I* km, const I* ibi, const u8* li, const R* gi,            \
                               const R* vi, int32_t* ibo_dev, u8* lo, R* go, R* vo, I* iret) {                            \
     api_plan_apply<R, I>((PlanHandle*)plan, stream, *km, ibi, li, gi, vi, ibo_dev, lo, go, vo, iret);                    \
+  }                                                                                                                      \
+  /* grid expanders (src/ipxwafs.F90:81, ipxwafs2.F90:92, ipxwafs3.F90:95, ipxetas.F90:90): every argument by reference */ \
+  void ipxwafs_##SFX(const I* idir, const I* nthin, const I* nfull, const I* km, const I* num_opt, I* opt, const I* len, \
+                     I* tthin, R* dthin, I* tfull, R* dfull, I* iret) {                                                  \
+    api_xwafs<R, I>(1, idir, nthin, nfull, km, num_opt, opt, len, tthin, dthin, nullptr, nullptr, tfull, dfull, nullptr, \
+                    nullptr, iret);                                                                                      \
+  }                                                                                                                      \
+  void ipxwafs2_##SFX(const I* idir, const I* nthin, const I* nfull, const I* km, const I* num_opt, I* opt, const I* len, \
+                      I* tthin, R* dthin, I* ibthin, u8* bthin, I* tfull, R* dfull, I* ibfull, u8* bfull, I* iret) {     \
+    api_xwafs<R, I>(2, idir, nthin, nfull, km, num_opt, opt, len, tthin, dthin, ibthin, bthin, tfull, dfull, ibfull,     \
+                    bfull, iret);                                                                                        \
+  }                                                                                                                      \
+  void ipxwafs3_##SFX(const I* idir, const I* nthin, const I* nfull, const I* km, const I* num_opt, I* opt, const I* len, \
+                      I* tthin, R* dthin, I* ibthin, u8* bthin, I* tfull, R* dfull, I* ibfull, u8* bfull, I* iret) {     \
+    api_xwafs<R, I>(3, idir, nthin, nfull, km, num_opt, opt, len, tthin, dthin, ibthin, bthin, tfull, dfull, ibfull,     \
+                    bfull, iret);                                                                                        \
+  }                                                                                                                      \
+  void ipxetas_##SFX(const I* idir, const I* numi, const I* len, const I* tin, const I* npi, const u8* bi, const R* di,  \
+                     I* numo, I* tout, const I* npo, u8* bo, R* dout, I* iret) {                                         \
+    /* staggered E grid (H / V points, scan 68 / 72) <-> full E grid (scan 64): the output template, then ipolates */   \
+    *iret = 0;                                                                                                           \
+    if (*numi != 1) { *iret = 1; return; }                                                                               \
+    const I scan = tin[18];                                                                                              \
+    int mode = 0; /* 1: staggered -> full, 2: full -> H, 3: full -> V */                                                 \
+    if ((scan == 68 || scan == 72) && (*idir < -2 || *idir > -1)) mode = 1;                                              \
+    else if (scan == 64 && *idir == -1) mode = 2;                                                                        \
+    else if (scan == 64 && *idir == -2) mode = 3;                                                                        \
+    *numo = *numi;                                                                                                       \
+    for (I q = 0; q < *len; q++) tout[q] = tin[q];                                                                       \
+    if (mode == 0) { *iret = 2; return; }                                                                                \
+    tout[18] = mode == 1 ? 64 : (mode == 2 ? 68 : 72);                                                                   \
+    tout[7] = mode == 1 ? tout[7] * 2 - 1 : (tout[7] + 1) / 2;                                                           \
+    if (tout[7] * tout[8] != *npo) { *iret = 3; return; }                                                                \
+    {                                                                                                                    \
+      i64 iscale = (i64)tout[9] * (i64)tout[10];                                                                         \
+      if (iscale == 0) iscale = 1000000;                                                                                 \
+      R dlons = (R)tout[16] / (R)iscale;                                                                                 \
+      dlons = dlons * (mode == 1 ? (R)0.5 : (R)2);                                                                       \
+      tout[16] = (I)nint_r<R>(dlons * (R)iscale);                                                                        \
+    }                                                                                                                    \
+    const I ip = 0, km = 1, ibi = 1;                                                                                     \
+    I ipopt[20] = {0}, ibo = 0, no = 0;                                                                                  \
+    try {                                                                                                                \
+      std::vector<R> rlat((size_t)*npo), rlon((size_t)*npo);                                                             \
+      ipolates_grib2_##SFX(&ip, ipopt, numi, tin, len, numo, tout, len, npi, npo, &km, &ibi, bi, di, &no, rlat.data(),   \
+                           rlon.data(), &ibo, bo, dout, iret);                                                           \
+    } catch (...) { *iret = (I)1001; }                                                                                   \
+    if (*iret != 0) return;                                                                                              \
+    const i64 im = (i64)tout[7], jm = (i64)tout[8];                                                                      \
+    for (i64 j = 1; j <= jm; j++) { /* the row ends copy their neighbours (ipxetas.F90:195-200) */                       \
+      bo[j * im - 1] = bo[j * im - 2]; dout[j * im - 1] = dout[j * im - 2];                                              \
+      bo[(j - 1) * im] = bo[(j - 1) * im + 1]; dout[(j - 1) * im] = dout[(j - 1) * im + 1];                              \
+    }                                                                                                                    \
   }                                                                                                                      \
   void gdswzd_##SFX(I num, const I* tmpl, I len, I iopt, I npts, R fill, R* xpts, R* ypts, R* rlon, R* rlat, I* nret,    \
                     R* crot, R* srot, R* xlon, R* xlat, R* ylon, R* ylat, R* area) {                                     \

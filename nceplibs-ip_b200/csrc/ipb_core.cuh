@@ -16,6 +16,7 @@
 #include "ipb_budget.cuh"
 #include "ipb_gtiles.cuh"
 #include "ipb_box.cuh"
+#include "ipb_expand.cuh"
 #include "ipb_state.h"
 
 namespace ipb {

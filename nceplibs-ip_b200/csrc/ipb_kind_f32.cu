@@ -6,6 +6,7 @@ namespace ipb {
 template void run<float>(bool, int, void*, i64, const i64*, const GridHost<float>&, const GridHost<float>&, i64, i64, i64, const i64*,
                   const u8*, const float*, const float*, i64&, float*, float*, float*, float*, i64*, u8*, float*, float*, i64&);
 template void run_gdswzd<float>(GridHost<float>, i64, i64, float, float*, float*, float*, float*, i64&, float*, float*, float*, float*, float*, float*, float*);
+template void run_xwafs<float>(int, bool, i64, const i64*, i64, i64, i64, i64, const i64*, const float*, const u8*, float*, u8*, i64*);
 template PlanHandle* plan_get<float>(bool, i64, const i64*, const GridHost<float>&, const GridHost<float>&, i64, i64, i64&, i64&);
 template int plan_geometry<float>(PlanHandle*, void*, float*, float*, float*, float*);
 template int plan_apply<float>(PlanHandle*, void*, i64, const i64*, const u8*, const float*, const float*, int*, u8*, float*, float*);

@@ -118,6 +118,42 @@ class IpLib:
         return dict(xpts=x, ypts=y, rlon=lon, rlat=lat, nret=int(nret[0]), **ex)
 
 
+    # ---- grid expanders (src/ipxwafs.F90:81, ipxwafs2.F90:92, ipxwafs3.F90:95, ipxetas.F90:90): every argument by reference ----
+    def ipxwafs(self, variant, idir, km, opt_pts, tmpl_thin, data_thin, tmpl_full, data_full, ib_thin=None, bitmap_thin=None, ib_full=None,
+                bitmap_full=None, nthin=3447, nfull=5329):
+        """variant 1 / 2 / 3 = ipxwafs / ipxwafs2 / ipxwafs3.  Arrays are copied; returns dict of every in/out argument."""
+        R = self.R
+        opt = self._ia(opt_pts)
+        tt, tf = self._ia(tmpl_thin), self._ia(tmpl_full)
+        dt = np.ascontiguousarray(data_thin, dtype=R).reshape(km, nthin).copy()
+        df = np.ascontiguousarray(data_full, dtype=R).reshape(km, nfull).copy()
+        sc = [self._ia([idir]), self._ia([nthin]), self._ia([nfull]), self._ia([km]), self._ia([opt.size]), self._ia([tt.size])]
+        iret = self._ia([-7])
+        if variant == 1:
+            self.fn("ipxwafs")(_p(sc[0]), _p(sc[1]), _p(sc[2]), _p(sc[3]), _p(sc[4]), _p(opt), _p(sc[5]), _p(tt), _p(dt), _p(tf), _p(df), _p(iret))
+            return dict(opt_pts=opt, tmpl_thin=tt, tmpl_full=tf, data_thin=dt, data_full=df, iret=int(iret[0]))
+        ibt = self._ia([0] * km if ib_thin is None else ib_thin, km)
+        ibf = self._ia([0] * km if ib_full is None else ib_full, km)
+        bt = np.ones((km, nthin), np.uint8) if bitmap_thin is None else np.ascontiguousarray(bitmap_thin, dtype=np.uint8).reshape(km, nthin).copy()
+        bf = np.ones((km, nfull), np.uint8) if bitmap_full is None else np.ascontiguousarray(bitmap_full, dtype=np.uint8).reshape(km, nfull).copy()
+        self.fn("ipxwafs2" if variant == 2 else "ipxwafs3")(_p(sc[0]), _p(sc[1]), _p(sc[2]), _p(sc[3]), _p(sc[4]), _p(opt), _p(sc[5]), _p(tt), _p(dt),
+                                                            _p(ibt), _p(bt), _p(tf), _p(df), _p(ibf), _p(bf), _p(iret))
+        return dict(opt_pts=opt, tmpl_thin=tt, tmpl_full=tf, data_thin=dt, data_full=df, ib_thin=ibt, ib_full=ibf, bitmap_thin=bt, bitmap_full=bf,
+                    iret=int(iret[0]))
+
+    def ipxetas(self, idir, igdtnumi, tmpl_in, bitmap_in, data_in, npts_out):
+        R = self.R
+        ti = self._ia(tmpl_in)
+        di = np.ascontiguousarray(data_in, dtype=R).ravel()
+        bi = np.ascontiguousarray(bitmap_in, dtype=np.uint8).ravel()
+        to = self._ia([0] * ti.size)
+        do = np.full(npts_out, -7777.0, R)
+        bo = np.full(npts_out, 7, np.uint8)
+        sc = [self._ia([idir]), self._ia([igdtnumi]), self._ia([ti.size]), self._ia([di.size]), self._ia([-7]), self._ia([npts_out]), self._ia([-7])]
+        self.fn("ipxetas")(_p(sc[0]), _p(sc[1]), _p(sc[2]), _p(ti), _p(sc[3]), _p(bi), _p(di), _p(sc[4]), _p(to), _p(sc[5]), _p(bo), _p(do), _p(sc[6]))
+        return dict(igdtnumo=int(sc[4][0]), tmpl_out=to, bitmap_out=bo, data_out=do, iret=int(sc[6][0]))
+
+
 PRODUCT_SO = os.path.join(HERE, "libipb200.so")
 
 _libs = {}

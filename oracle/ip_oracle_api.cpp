@@ -6,6 +6,7 @@
 // (src/ipolates.F90:158,293,587,808; src/ipolatev.F90:382,565,680,832; src/gdswzd_c.F90:173,259),
 // every argument by reference except the by-value scalars of gdswzd / gdswzd_grib1.
 #include "ip_oracle_interp.hpp"
+#include "ip_oracle_expand.hpp"
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -85,8 +86,48 @@ void gdswzd_any(bool grib2, I num, const I* dsc, I len, I iopt, I npts, R fill, 
 
 }  // namespace
 
+template <class R, class I>
+void ipxwafs_c(int variant, const I* idir, const I* nthin, const I* nfull, const I* km, const I* num_opt, I* opt, const I* len, I* tthin, R* dthin,
+               I* ibthin, u8* bthin, I* tfull, R* dfull, I* ibfull, u8* bfull, I* iret) {
+  auto o = widen(opt, *num_opt), tt = widen(tthin, *len), tf = widen(tfull, *len);
+  std::vector<i64> it(*km > 0 ? *km : 1, 0), ifu(*km > 0 ? *km : 1, 0);
+  if (variant != 1) for (i64 k = 0; k < *km; k++) { it[k] = ibthin[k]; ifu[k] = ibfull[k]; }
+  i64 ir = 0;
+  ipxwafs_any<R>(variant, *idir, *nthin, *nfull, *km, *num_opt, o.data(), *len, tt.data(), dthin, it.data(), bthin, tf.data(), dfull, ifu.data(), bfull, ir);
+  *iret = (I)ir;
+  for (i64 q = 0; q < *num_opt; q++) opt[q] = (I)o[q];
+  for (i64 q = 0; q < *len; q++) { tthin[q] = (I)tt[q]; tfull[q] = (I)tf[q]; }
+  if (variant != 1) for (i64 k = 0; k < *km; k++) { ibthin[k] = (I)it[k]; ibfull[k] = (I)ifu[k]; }
+}
+template <class R, class I>
+void ipxetas_c(const I* idir, const I* numi, const I* len, const I* tin, const I* npi, const u8* bi, const R* di, I* numo, I* tout, const I* npo,
+               u8* bo, R* dout, I* iret) {
+  auto ti = widen(tin, *len);
+  std::vector<i64> to(*len, 0);
+  i64 no = 0, ir = 0;
+  ipxetas<R>(*idir, *numi, *len, ti.data(), *npi, bi, di, no, to.data(), *npo, bo, dout, ir);
+  *iret = (I)ir;
+  if (ir != 1 || *numi == 1) { *numo = (I)no; for (i64 q = 0; q < *len; q++) tout[q] = (I)to[q]; }
+}
+
 #define ORACLE_KIND(SFX, R, I)                                                                                          \
   extern "C" {                                                                                                          \
+  void oracle_ipxwafs_##SFX(const I* idir, const I* nthin, const I* nfull, const I* km, const I* num_opt, I* opt, const I* len, I* tthin,  \
+                            R* dthin, I* tfull, R* dfull, I* iret) {                                                    \
+    ipxwafs_c<R, I>(1, idir, nthin, nfull, km, num_opt, opt, len, tthin, dthin, nullptr, nullptr, tfull, dfull, nullptr, nullptr, iret);   \
+  }                                                                                                                     \
+  void oracle_ipxwafs2_##SFX(const I* idir, const I* nthin, const I* nfull, const I* km, const I* num_opt, I* opt, const I* len, I* tthin, \
+                             R* dthin, I* ibthin, u8* bthin, I* tfull, R* dfull, I* ibfull, u8* bfull, I* iret) {       \
+    ipxwafs_c<R, I>(2, idir, nthin, nfull, km, num_opt, opt, len, tthin, dthin, ibthin, bthin, tfull, dfull, ibfull, bfull, iret);         \
+  }                                                                                                                     \
+  void oracle_ipxwafs3_##SFX(const I* idir, const I* nthin, const I* nfull, const I* km, const I* num_opt, I* opt, const I* len, I* tthin, \
+                             R* dthin, I* ibthin, u8* bthin, I* tfull, R* dfull, I* ibfull, u8* bfull, I* iret) {       \
+    ipxwafs_c<R, I>(3, idir, nthin, nfull, km, num_opt, opt, len, tthin, dthin, ibthin, bthin, tfull, dfull, ibfull, bfull, iret);         \
+  }                                                                                                                     \
+  void oracle_ipxetas_##SFX(const I* idir, const I* numi, const I* len, const I* tin, const I* npi, const u8* bi, const R* di, I* numo,    \
+                            I* tout, const I* npo, u8* bo, R* dout, I* iret) {                                          \
+    ipxetas_c<R, I>(idir, numi, len, tin, npi, bi, di, numo, tout, npo, bo, dout, iret);                                \
+  }                                                                                                                     \
   void oracle_ipolates_grib2_##SFX(const I* ip, const I* ipopt, const I* numi, const I* tmpli, const I* leni,           \
                                    const I* numo, const I* tmplo, const I* leno, const I* mi, const I* mo, const I* km, \
                                    const I* ibi, const u8* li, const R* gi, I* no, R* rlat, R* rlon, I* ibo, u8* lo,   \

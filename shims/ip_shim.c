@@ -47,3 +47,22 @@ void ipolatev_grib2(G2_ARGS, V_TAIL) { K(ipolatev_grib2)(G2_PASS, V_PASS); }
 void ipolatev_grib2_single_field(G2_ARGS, V_TAIL) { K(ipolatev_grib2_single_field)(G2_PASS, V_PASS); }
 void ipolatev_grib1(G1_ARGS, V_TAIL) { K(ipolatev_grib1)(G1_PASS, V_PASS); }
 void ipolatev_grib1_single_field(G1_ARGS, V_TAIL) { K(ipolatev_grib1_single_field)(G1_PASS, V_PASS); }
+
+/* The grid expanders are plain external subroutines in the reference (src/ipxwafs.F90:81, ipxwafs2.F90:92,
+ * ipxwafs3.F90:95, ipxetas.F90:90), so a Fortran caller links the compiler-mangled names: lower case plus one
+ * underscore (gfortran, ifort, nvfortran).  No character arguments, hence no hidden lengths. */
+#define XW_HEAD const ip_int *idir, const ip_int *nthin, const ip_int *nfull, const ip_int *km, const ip_int *num_opt, ip_int *opt, \
+                const ip_int *len, ip_int *tthin, ip_real *dthin
+void ipxwafs_(XW_HEAD, ip_int* tfull, ip_real* dfull, ip_int* iret) {
+  K(ipxwafs)(idir, nthin, nfull, km, num_opt, opt, len, tthin, dthin, tfull, dfull, iret);
+}
+void ipxwafs2_(XW_HEAD, ip_int* ibthin, ip_logical* bthin, ip_int* tfull, ip_real* dfull, ip_int* ibfull, ip_logical* bfull, ip_int* iret) {
+  K(ipxwafs2)(idir, nthin, nfull, km, num_opt, opt, len, tthin, dthin, ibthin, bthin, tfull, dfull, ibfull, bfull, iret);
+}
+void ipxwafs3_(XW_HEAD, ip_int* ibthin, ip_logical* bthin, ip_int* tfull, ip_real* dfull, ip_int* ibfull, ip_logical* bfull, ip_int* iret) {
+  K(ipxwafs3)(idir, nthin, nfull, km, num_opt, opt, len, tthin, dthin, ibthin, bthin, tfull, dfull, ibfull, bfull, iret);
+}
+void ipxetas_(const ip_int* idir, const ip_int* numi, const ip_int* len, const ip_int* tin, const ip_int* npi, const ip_logical* bi,
+              const ip_real* di, ip_int* numo, ip_int* tout, const ip_int* npo, ip_logical* bo, ip_real* dout, ip_int* iret) {
+  K(ipxetas)(idir, numi, len, tin, npi, bi, di, numo, tout, npo, bo, dout, iret);
+}

@@ -36,7 +36,8 @@ def test_library_exports_every_declared_symbol():
     for kind in "4d8":
         for stem in ("ipolates_grib2", "ipolates_grib1", "ipolates_grib2_single_field", "ipolates_grib1_single_field",
                      "ipolatev_grib2", "ipolatev_grib1", "ipolatev_grib2_single_field", "ipolatev_grib1_single_field",
-                     "gdswzd", "gdswzd_grib1", "ipgpu_ipolates_grib2_dev", "ipgpu_ipolatev_grib2_dev"):
+                     "gdswzd", "gdswzd_grib1", "ipgpu_ipolates_grib2_dev", "ipgpu_ipolatev_grib2_dev", "ipxwafs", "ipxwafs2", "ipxwafs3",
+                     "ipxetas"):
             assert f"{stem}_{kind}" in names, f"{stem}_{kind} not declared"
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
@@ -133,6 +134,7 @@ def test_kind_shims_export_the_reference_symbols():
     pkg.build_library()
     here = os.path.dirname(pkg.PRODUCT_SO)
     want = ["gdswzd", "gdswzd_grib1"] + [f"ipolate{sv}_grib{g}{sf}" for sv in "sv" for g in "12" for sf in ("", "_single_field")]
+    want += ["ipxwafs_", "ipxwafs2_", "ipxwafs3_", "ipxetas_"]      # external subroutines: the Fortran-mangled names
     for k in "4d8":
         r = subprocess.run(["nm", "-D", "--defined-only", os.path.join(here, f"libip_{k}.so")], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
