@@ -25,7 +25,7 @@ pkg = importlib.import_module("nceplibs-ip_b200")
 def _declared_symbols():
     h = open(os.path.join(ROOT, "include", "ipb200.h")).read()
     h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
-    return sorted(set(re.findall(r"\b((?:ipolate[sv]|gdswzd|ipgpu)_[a-z0-9_]+|gdswzd_[4d8])\s*\(", h)))
+    return sorted(set(re.findall(r"\b((?:ipolate[sv]|gdswzd|ipgpu|ipxwafs[23]?|ipxetas)_[a-z0-9_]+|gdswzd_[4d8])\s*\(", h)))
 
 
 def test_library_exports_every_declared_symbol():
