@@ -51,6 +51,16 @@ void* DBuf::get(size_t bytes) {
   return p;
 }
 void DBuf::release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+void* HBuf::get(size_t bytes) {
+  if (bytes > cap) {
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    IPB_CUDA_API(cudaHostAlloc(&p, bytes, cudaHostAllocPortable));
+    cap = bytes;
+  }
+  return p;
+}
+void HBuf::release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 
 Runtime& rt() { static Runtime r; return r; }
 AllocCtx& alloc_ctx() { static thread_local AllocCtx c; return c; }
@@ -455,7 +465,7 @@ void ipgpu_plan_clear() {
     std::lock_guard<std::mutex> lock(d->mu);
     DeviceGuard guard(d->device);
     d->cache.clear();
-    for (int i = 0; i < 2; i++) { Work& w = d->work[i]; w.gi.release(); w.vi.release(); w.li.release(); w.go.release(); w.vo.release(); w.lo.release(); w.ints.release(); }
+    for (int i = 0; i < 2; i++) { Work& w = d->work[i]; w.gi.release(); w.vi.release(); w.li.release(); w.go.release(); w.vo.release(); w.lo.release(); w.ints.release(); w.lbits.release(); w.hbits.release(); }
   }
 }
 long long ipgpu_plan_count() {

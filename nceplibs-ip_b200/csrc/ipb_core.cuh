@@ -106,6 +106,9 @@ void launch_apply(const Plan<R>& P, bool vec, FieldArgs<R> a, cudaStream_t st) {
 }
 
 // ibo(k) = ibi(k), forced to 1 where any lo is false; then the pole fix for lat-lon outputs.
+// (not cudaMemsetAsync: a memset may be given to a copy engine, where it queues behind the other chunk's 8 ms go copy
+// and holds this chunk's kernels that long)
+static __global__ void k_zero_ints(int n, int* p) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = 0; }
 static __global__ void k_ibo(int kc, const int* __restrict__ ibi, const int* __restrict__ flag, int* ibo) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < kc) ibo[k] = flag[k] ? 1 : ibi[k];
@@ -126,6 +129,56 @@ void launch_post(const Plan<R>& P, bool vec, const FieldArgs<R>& a, int* d_ibo, 
       g_launches++;
     }
   }
+}
+
+// ---- lo across PCIe as one bit per point -----------------------------------------------------------------------------
+// The host-pointer call is bound by the device -> host link (go + lo: 5 bytes per point·field in the _4 kind), and lo is a
+// fifth of that while it carries one bit.  The device packs lo (bit i of word w = point 32 w + i) and notes per field
+// whether any point is false; the host thread(s) write the caller's LOGICAL*1 array from that: memset for a field
+// without a false point, a table lookup per byte of bits otherwise.  The bytes the caller sees are the same.
+static __global__ void __launch_bounds__(256)
+k_pack_lo(const u8* __restrict__ lo, int mo, int no, int nw, unsigned* __restrict__ bits, int* __restrict__ hasfalse) {
+  const int lane = threadIdx.x & 31, k = blockIdx.y;
+  const int wbase = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+  if (wbase >= nw) return;
+  const u8* __restrict__ p = lo + (size_t)k * mo;
+  unsigned mine = 0, bad = 0;
+#pragma unroll 4
+  for (int i = 0; i < 32; i++) {
+    if (wbase + i >= nw) break;
+    const int n = (wbase + i) * 32 + lane;
+    const bool in = n < no;
+    const bool t = in && p[n] != 0;
+    const unsigned word = __ballot_sync(0xffffffffu, t);
+    bad |= __ballot_sync(0xffffffffu, in && !t);
+    if (lane == i) mine = word;
+  }
+  if (wbase + lane < nw) bits[(size_t)k * nw + wbase + lane] = mine;
+  if (bad != 0 && lane == 0 && hasfalse[k] == 0) hasfalse[k] = 1;
+}
+
+inline void expand_lo_fields(u8* lo, i64 mo, i64 no, i64 kbeg, i64 kend, i64 kstep, const unsigned* bits, i64 nw, const int* hasfalse) {
+  static const std::vector<unsigned long long> lut = [] {
+    std::vector<unsigned long long> t(256);
+    for (int b = 0; b < 256; b++) { unsigned long long v = 0; for (int j = 0; j < 8; j++) v |= (unsigned long long)((b >> j) & 1) << (8 * j); t[b] = v; }
+    return t;
+  }();
+  for (i64 k = kbeg; k < kend; k += kstep) {
+    u8* o = lo + (size_t)k * mo;
+    if (!hasfalse[k]) { memset(o, 1, (size_t)no); continue; }
+    const unsigned char* b = reinterpret_cast<const unsigned char*>(bits + (size_t)k * nw);
+    const i64 full = no / 8;
+    for (i64 q = 0; q < full; q++) memcpy(o + 8 * q, &lut[b[q]], 8);   // little-endian hosts (x86-64, aarch64)
+    for (i64 n = full * 8; n < no; n++) o[n] = (u8)((b[n >> 3] >> (n & 7)) & 1);
+  }
+}
+inline void expand_lo(u8* lo, i64 mo, i64 no, i64 kn, const unsigned* bits, i64 nw, const int* hasfalse, int threads) {
+  const int T = (int)std::max<i64>(1, std::min<i64>(threads, (kn * no) >> 20));   // a thread per MiB of lo at least
+  if (T <= 1) { expand_lo_fields(lo, mo, no, 0, kn, 1, bits, nw, hasfalse); return; }
+  std::vector<std::thread> th;
+  for (int t = 1; t < T; t++) th.emplace_back(expand_lo_fields, lo, mo, no, (i64)t, kn, (i64)T, bits, nw, hasfalse);
+  expand_lo_fields(lo, mo, no, 0, kn, T, bits, nw, hasfalse);
+  for (auto& x : th) x.join();
 }
 
 // ---- options and plans -----------------------------------------------------------------------------
@@ -259,23 +312,44 @@ void run_on(int device, bool stats, bool vec, int dev, void* user_stream, i64 ip
       if (km > 1 && kc >= km) kc = (km + 1) / 2;  // at least two chunks so copies and kernels overlap
       IPB_CUDA(cudaStreamSynchronize(st0));        // plan ready before the second stream uses it
       size_t win_lo = 0, win_n = (size_t)mi;
-      if (mspiral <= 1 && !(method == M_BILINEAR && mspiral > 0)) {
+      static const bool h2d_full = getenv("IPB_H2D_FULL") && atoi(getenv("IPB_H2D_FULL")) != 0;   // A/B: whole fields, plain copies
+      if (!h2d_full && mspiral <= 1 && !(method == M_BILINEAR && mspiral > 0)) {
         if (P->src_hi >= P->src_lo) { win_lo = (size_t)P->src_lo - 1; win_n = (size_t)(P->src_hi - P->src_lo + 1); }
         else { win_lo = 0; win_n = 0; }
       }
+      // lo crosses the link packed (k_pack_lo) unless IPB_LO_BYTES=1 asks for the plain byte copy
+      static const bool lo_bytes = getenv("IPB_LO_BYTES") && atoi(getenv("IPB_LO_BYTES")) != 0;
+      static const int host_threads = getenv("IPB_HOST_THREADS") ? std::max(1, atoi(getenv("IPB_HOST_THREADS")))
+                                                                 : (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+      const int nshard = (int)std::max<size_t>(1, RT.shard.size());
+      const int lo_threads = std::max(1, host_threads / nshard);
+      const i64 nw = ((i64)NO + 31) / 32;
+      // Everything a chunk brings back besides go sits in the slot's PINNED staging (ibo, packed lo): a device -> host copy
+      // into pageable memory would hold the host until the chunk has drained, and the two chunks would never overlap.
+      struct Pending { i64 k0 = 0, kn = 0; bool on = false; const int* ints = nullptr; const unsigned* bits = nullptr; } pend[2];
+      auto finish_chunk = [&](Pending q) {   // the chunk's stream has drained
+        if (!q.on) return;
+        for (i64 k = 0; k < q.kn; k++) ibo32[q.k0 + k] = q.ints[k];
+        if (q.bits) expand_lo(lo + (size_t)q.k0 * mo, mo, NO, q.kn, q.bits, nw, q.ints + q.kn, lo_threads);
+      };
+      // two staging halves per slot: the next chunk is queued on the slot BEFORE the host turns to the finished one's lo
+      const size_t stage_bytes = (size_t)3 * kc * sizeof(int) + (lo_bytes ? 0 : (size_t)kc * nw * sizeof(unsigned));
+      i64 chunk_no = 0;
       int ci = 0;
       for (i64 k0 = 0; k0 < km; k0 += kc, ci ^= 1) {
         const i64 kn = std::min(kc, km - k0);
         cudaStream_t s = DS.stream[ci];
         Work& w = DS.work[ci];
         IPB_CUDA(cudaStreamSynchronize(s));  // buffers of this slot are free again
+        const Pending done = pend[ci];
+        pend[ci].on = false;
         R* d_gi = (R*)w.gi.get((size_t)kn * mi * sizeof(R));
         R* d_vi = vec ? (R*)w.vi.get((size_t)kn * mi * sizeof(R)) : nullptr;
         u8* d_li = any_mask ? (u8*)w.li.get((size_t)kn * mi) : nullptr;
         R* d_go = (R*)w.go.get((size_t)kn * mo * sizeof(R));
         R* d_vo = vec ? (R*)w.vo.get((size_t)kn * mo * sizeof(R)) : nullptr;
         u8* d_lo = (u8*)w.lo.get((size_t)kn * mo);
-        int* d_int = (int*)w.ints.get((size_t)kn * 3 * sizeof(int));
+        int* d_int = (int*)w.ints.get((size_t)kn * 4 * sizeof(int));
         // only the window of the input field the plan refers to crosses PCIe (the spiral searches can leave it)
         h2d += (long long)win_n * kn * (sizeof(R) * (vec ? 2 : 1) + (any_mask ? 1 : 0));
         if (win_lo == 0 && win_n == (size_t)mi) {
@@ -287,26 +361,50 @@ void run_on(int device, bool stats, bool vec, int dev, void* user_stream, i64 ip
           if (vec) IPB_CUDA(cudaMemcpy2DAsync(d_vi + win_lo, mi * sizeof(R), vi + (size_t)k0 * mi + win_lo, mi * sizeof(R), win_n * sizeof(R), kn, cudaMemcpyHostToDevice, s));
           if (any_mask) IPB_CUDA(cudaMemcpy2DAsync(d_li + win_lo, mi, li + (size_t)k0 * mi + win_lo, mi, win_n, kn, cudaMemcpyHostToDevice, s));
         }
-        IPB_CUDA(cudaMemcpyAsync(d_int, ibi32.data() + k0, kn * sizeof(int), cudaMemcpyHostToDevice, s));
-        IPB_CUDA(cudaMemsetAsync(d_int + kn, 0, kn * sizeof(int), s));
+        const size_t nbits = lo_bytes ? 0 : (size_t)kn * nw * sizeof(unsigned);
+        int* h_int = (int*)((unsigned char*)w.hbits.get(2 * stage_bytes) + ((chunk_no >> 1) & 1) * stage_bytes);   // [ibi | ibo | field has a false point][packed lo]
+        for (i64 k = 0; k < kn; k++) h_int[k] = ibi32[k0 + k];
+        IPB_CUDA(cudaMemcpyAsync(d_int, h_int, kn * sizeof(int), cudaMemcpyHostToDevice, s));
+        k_zero_ints<<<nblk(3 * kn, 128), 128, 0, s>>>((int)(3 * kn), d_int + kn);   // flag, ibo, has-a-false-point
         FieldArgs<R> a{NO, (int)mi, (int)mo, (int)kn, d_gi, d_vi, d_li, d_int, d_go, d_vo, d_lo, d_int + kn, pmp, (int)mcon, (int)mspiral};
         launch_apply<R>(*P, vec, a, s);
         launch_post<R>(*P, vec, a, d_int + 2 * kn, s);
+        // The small results first (packed lo, ibo), the big go copy last: a small copy queued behind it would wait for the
+        // OTHER chunk's go on the copy engine and hold this slot — and the next chunk's kernels — that long.
+        if (!lo_bytes) {
+          unsigned* d_bits = (unsigned*)w.lbits.get(nbits);
+          k_pack_lo<<<dim3(nblk(nblk(nw, 32), 8), (unsigned)kn), 256, 0, s>>>(d_lo, (int)mo, NO, (int)nw, d_bits, d_int + 3 * kn);
+          g_launches++;
+          IPB_CUDA(cudaMemcpyAsync(h_int + 3 * kn, d_bits, nbits, cudaMemcpyDeviceToHost, s));
+          d2h += (long long)nbits;
+        }
+        // ibo and the has-a-false-point flags are neighbours on the device (d_int + 2 kn, + 3 kn): one copy
+        IPB_CUDA(cudaMemcpyAsync(h_int + kn, d_int + 2 * kn, (lo_bytes ? 1 : 2) * kn * sizeof(int), cudaMemcpyDeviceToHost, s));
+        d2h += (long long)((lo_bytes ? 1 : 2) * kn * sizeof(int));
+        if (lo_bytes) {
+          d2h += (long long)NO * kn;
+          if (NO == mo) IPB_CUDA(cudaMemcpyAsync(lo + (size_t)k0 * mo, d_lo, (size_t)kn * mo, cudaMemcpyDeviceToHost, s));
+          else IPB_CUDA(cudaMemcpy2DAsync(lo + (size_t)k0 * mo, mo, d_lo, mo, NO, kn, cudaMemcpyDeviceToHost, s));
+        }
         // only the first NO points of each field are defined (the reference leaves the rest untouched)
-        d2h += (long long)NO * kn * (sizeof(R) * (vec ? 2 : 1) + 1);
+        d2h += (long long)NO * kn * (sizeof(R) * (vec ? 2 : 1));
         if (NO == mo) {
           IPB_CUDA(cudaMemcpyAsync(go + (size_t)k0 * mo, d_go, (size_t)kn * mo * sizeof(R), cudaMemcpyDeviceToHost, s));
           if (vec) IPB_CUDA(cudaMemcpyAsync(vo + (size_t)k0 * mo, d_vo, (size_t)kn * mo * sizeof(R), cudaMemcpyDeviceToHost, s));
-          IPB_CUDA(cudaMemcpyAsync(lo + (size_t)k0 * mo, d_lo, (size_t)kn * mo, cudaMemcpyDeviceToHost, s));
         } else {
           IPB_CUDA(cudaMemcpy2DAsync(go + (size_t)k0 * mo, mo * sizeof(R), d_go, mo * sizeof(R), NO * sizeof(R), kn, cudaMemcpyDeviceToHost, s));
           if (vec) IPB_CUDA(cudaMemcpy2DAsync(vo + (size_t)k0 * mo, mo * sizeof(R), d_vo, mo * sizeof(R), NO * sizeof(R), kn, cudaMemcpyDeviceToHost, s));
-          IPB_CUDA(cudaMemcpy2DAsync(lo + (size_t)k0 * mo, mo, d_lo, mo, NO, kn, cudaMemcpyDeviceToHost, s));
         }
-        IPB_CUDA(cudaMemcpyAsync(ibo32.data() + k0, d_int + 2 * kn, kn * sizeof(int), cudaMemcpyDeviceToHost, s));
+        pend[ci].k0 = k0; pend[ci].kn = kn; pend[ci].on = true;
+        pend[ci].ints = h_int + kn; pend[ci].bits = lo_bytes ? nullptr : reinterpret_cast<const unsigned*>(h_int + 3 * kn);
+        chunk_no++;
+        finish_chunk(done);
       }
-      IPB_CUDA(cudaStreamSynchronize(DS.stream[0]));
-      IPB_CUDA(cudaStreamSynchronize(DS.stream[1]));
+      // the older chunk first: its lo is written while the newer one's go is still on the link
+      IPB_CUDA(cudaStreamSynchronize(DS.stream[ci]));
+      finish_chunk(pend[ci]);
+      IPB_CUDA(cudaStreamSynchronize(DS.stream[ci ^ 1]));
+      finish_chunk(pend[ci ^ 1]);
     }
     for (i64 k = 0; k < km; k++) ibo[k] = ibo32[k];
   } else {

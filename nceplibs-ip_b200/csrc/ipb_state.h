@@ -22,7 +22,12 @@ struct DBuf {  // growable device scratch
   void* get(size_t bytes);
   void release();
 };
-struct Work { DBuf gi, vi, li, go, vo, lo, ints; };
+struct HBuf {  // growable pinned host staging
+  void* p = nullptr; size_t cap = 0;
+  void* get(size_t bytes);
+  void release();
+};
+struct Work { DBuf gi, vi, li, go, vo, lo, ints, lbits; HBuf hbits; };
 
 struct CacheEntry { std::vector<i64> key; std::shared_ptr<void> plan; int kind; size_t bytes; unsigned long long stamp; };
 

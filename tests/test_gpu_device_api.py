@@ -299,6 +299,33 @@ def test_host_call_sharded_over_devices():
         assert np.array_equal(v1[k], vm[k]), k
 
 
+@pytest.mark.parametrize("kind", ["4", "d"])
+@pytest.mark.parametrize("ip", [0, 2, 3])
+def test_host_call_lo_crosses_the_link_packed(kind, ip):
+    """Host-pointer calls bring lo back as one bit per point and rebuild the caller's LOGICAL*1 array on the host
+    (k_pack_lo / expand_lo): fields without a false point, fields with holes, mo > no (the tail stays untouched), a point
+    count that is no multiple of 8 or 32, and many chunks in flight one after the other."""
+    P, O = product(kind), oracle(kind)
+    gin, gout = ic.g2_input(kind), ic.g2_templates(kind)["218"]
+    mi, no, km = ic.npts_of(gin), ic.npts_of(gout), 9
+    mo = no + 37
+    rng = np.random.default_rng(31 + ip)
+    g = np.stack([ic.inputs()["snoalb"] + rng.standard_normal(mi) for k in range(km)]).astype(P.R)
+    li = (rng.random((km, mi)) < 0.7).astype(np.uint8)
+    li[4] = 1                                    # a field that announces a bitmap and has no hole
+    ibi = [0, 1, 0, 1, 1, 0, 1, 1, 0]
+    P.lib.ipgpu_set_chunk_bytes(C.c_longlong(1))   # one field per chunk
+    try:
+        a = P.ipolates(ip, [-1] * 20, gin, gout, mi, mo, km, ibi, li, g)
+    finally:
+        P.lib.ipgpu_set_chunk_bytes(C.c_longlong(768 << 20))
+    b = O.ipolates(ip, [-1] * 20, gin, gout, mi, mo, km, ibi, li, g)
+    assert a["iret"] == 0 and a["no"] == b["no"] == no
+    assert np.array_equal(a["lo"], b["lo"]) and np.array_equal(a["ibo"], b["ibo"])
+    assert (a["lo"][:, no:] == 7).all()          # beyond no the caller's bytes are left alone
+    assert a["lo"][0].min() == 1 and a["lo"][1].min() == 0
+
+
 @pytest.mark.parametrize("lsize,sfx", [("4", "4"), ("D", "d"), ("8", "8")])
 def test_c_caller_links_the_kind_shims(lsize, sfx, tmp_path):
     """A C program written against the reference's C interface (unsuffixed gdswzd / gdswzd_grib1 / ipolates_grib2, include/iplib.h)
