@@ -681,7 +681,7 @@ def run_e2e(args, wl, lib, L, torch, dist, dev, world, gin, gout, mi, mo, km, no
             "pcie_gbs_peak": {"h2d": lp[0].value, "d2h": lp[1].value, "both_directions": lp[2].value, "how": "ipgpu_link_probe, 256 MiB pinned copies"},
             "link_floor_ms": floor_ms, "frac_of_link_ceiling": floor_ms / (dt * 1e3), "numa_node_of_gpu": int(L.ipgpu_device_numa_node()),
             "devices_in_library": ndev_lib,
-            "api": ("ipolatev_grib2_" if vec else "ipolates_grib2_") + wl["kind"] + " (host pointers, pinned; only the source window the plan references is copied in)",
+            "api": ("ipolatev_grib2_" if vec else "ipolates_grib2_") + wl["kind"] + " (host pointers, pinned; only the source window the plan references is copied in; lo comes back as one bit per point and is rebuilt by host threads inside the call)",
             "matches_device_path": ok}
 
 
