@@ -600,6 +600,8 @@ def run_e2e(args, wl, lib, L, torch, dist, dev, world, gin, gout, mi, mo, km, no
 
     def pinned(shape, dtype):
         n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        if getattr(args, "pageable", False):   # what a Fortran caller has: ordinary memory, staged by the library
+            return np.zeros(shape, dtype), None
         p = L.ipgpu_host_alloc(C.c_longlong(n))
         if not p:
             raise MemoryError("cudaMallocHost failed")
@@ -667,7 +669,8 @@ def run_e2e(args, wl, lib, L, torch, dist, dev, world, gin, gout, mi, mo, km, no
     if ndev_lib > 1:
         L.ipgpu_set_devices(C.c_int(1))
     for p_ in bufs:
-        L.ipgpu_host_free(C.c_void_p(p_))
+        if p_:
+            L.ipgpu_host_free(C.c_void_p(p_))
     # the ceiling of this rank's host link, measured in this process with the same pinned allocator (one large copy per
     # direction, then both at once); the call is D2H dominated, so its floor is d2h bytes / d2h rate
     lp = [C.c_double(0), C.c_double(0), C.c_double(0)]
@@ -681,6 +684,7 @@ def run_e2e(args, wl, lib, L, torch, dist, dev, world, gin, gout, mi, mo, km, no
             "pcie_gbs_peak": {"h2d": lp[0].value, "d2h": lp[1].value, "both_directions": lp[2].value, "how": "ipgpu_link_probe, 256 MiB pinned copies"},
             "link_floor_ms": floor_ms, "frac_of_link_ceiling": floor_ms / (dt * 1e3), "numa_node_of_gpu": int(L.ipgpu_device_numa_node()),
             "devices_in_library": ndev_lib,
+            "host_arrays": "pageable (staged by the library)" if getattr(args, "pageable", False) else "pinned (ipgpu_host_alloc)",
             "api": ("ipolatev_grib2_" if vec else "ipolates_grib2_") + wl["kind"] + " (host pointers, pinned; only the source window the plan references is copied in; lo comes back as one bit per point and is rebuilt by host threads inside the call)",
             "matches_device_path": ok}
 
@@ -696,6 +700,7 @@ def main():
     ap.add_argument("--kind", default="", choices=["", "4", "d", "8"], help="build kind override (default: the workload's)")
     ap.add_argument("--mask", type=int, default=-1, help="1: every field carries the land-mask bitmap, 0: none (default: the workload's)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--pageable", action="store_true", help="e2e with ordinary (pageable) host arrays instead of pinned ones")
     ap.add_argument("--no-secondary", action="store_true", help="skip the budget configuration attached to the default (bilinear) line")
     ap.add_argument("--chunk-mib", type=int, default=0, help="staging size per in-flight chunk of the host-pointer path (default: the library's, 768)")
     ap.add_argument("--no-cpu", action="store_true")

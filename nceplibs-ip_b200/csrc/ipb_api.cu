@@ -465,7 +465,7 @@ void ipgpu_plan_clear() {
     std::lock_guard<std::mutex> lock(d->mu);
     DeviceGuard guard(d->device);
     d->cache.clear();
-    for (int i = 0; i < 2; i++) { Work& w = d->work[i]; w.gi.release(); w.vi.release(); w.li.release(); w.go.release(); w.vo.release(); w.lo.release(); w.ints.release(); w.lbits.release(); w.hbits.release(); }
+    for (int i = 0; i < 2; i++) { Work& w = d->work[i]; w.gi.release(); w.vi.release(); w.li.release(); w.go.release(); w.vo.release(); w.lo.release(); w.ints.release(); w.lbits.release(); w.hbits.release(); w.hin.release(); w.hout.release(); }
   }
 }
 long long ipgpu_plan_count() {

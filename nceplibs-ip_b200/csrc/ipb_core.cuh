@@ -181,6 +181,37 @@ inline void expand_lo(u8* lo, i64 mo, i64 no, i64 kn, const unsigned* bits, i64 
   for (auto& x : th) x.join();
 }
 
+// rows of `width` bytes from src (pitch spitch) to dst (pitch dpitch) on `threads` host threads: the byte range is cut
+// into equal pieces, whatever the row count
+inline void copy_rows_range(unsigned char* dst, size_t dpitch, const unsigned char* src, size_t spitch, size_t width, size_t b0, size_t b1) {
+  while (b0 < b1) {
+    const size_t r = b0 / width, off = b0 - r * width, n = std::min(width - off, b1 - b0);
+    memcpy(dst + r * dpitch + off, src + r * spitch + off, n);
+    b0 += n;
+  }
+}
+inline void copy_rows(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows, int threads) {
+  const size_t total = width * rows;
+  if (total == 0) return;
+  const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, total >> 20));
+  unsigned char* d = static_cast<unsigned char*>(dst);
+  const unsigned char* q = static_cast<const unsigned char*>(src);
+  if (T <= 1) { copy_rows_range(d, dpitch, q, spitch, width, 0, total); return; }
+  const size_t piece = (total + T - 1) / T;
+  std::vector<std::thread> th;
+  for (int t = 1; t < T; t++) th.emplace_back(copy_rows_range, d, dpitch, q, spitch, width, std::min(total, t * piece), std::min(total, (t + 1) * piece));
+  copy_rows_range(d, dpitch, q, spitch, width, 0, std::min(total, piece));
+  for (auto& x : th) x.join();
+}
+// is p memory the copy engines can reach directly (cudaHostAlloc / cudaHostRegister / managed)?  An ordinary Fortran or
+// C array is not: the driver would stage every copy through its own small buffer and hold the host meanwhile.
+inline bool host_ptr_pinned(const void* p) {
+  if (!p) return true;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged || at.type == cudaMemoryTypeDevice;
+}
+
 // ---- options and plans -----------------------------------------------------------------------------
 // option decode of the stencil methods (bilinear_interp_mod.F90:110-115, bicubic :117-122, neighbor :135); the budget
 // family's threshold comes from its plan (decode_budget_opt).  Returns iret (0 or 32).
@@ -310,6 +341,12 @@ void run_on(int device, bool stats, bool vec, int dev, void* user_stream, i64 ip
       const size_t per_field = ((size_t)mi + (size_t)mo) * sizeof(R) * (vec ? 2 : 1) + (any_mask ? mi : 0) + mo;
       i64 kc = std::max<i64>(1, std::min<i64>(km, (i64)(RT.chunk_bytes / std::max<size_t>(per_field, 1))));
       if (km > 1 && kc >= km) kc = (km + 1) / 2;  // at least two chunks so copies and kernels overlap
+      // Pageable caller arrays (what a Fortran caller has) go through the slot's own pinned staging, copied by host threads:
+      // left to the driver such copies run at a fraction of the link rate and hold the host, so nothing overlaps.
+      static const bool no_stage = getenv("IPB_NO_STAGE") && atoi(getenv("IPB_NO_STAGE")) != 0;
+      const bool stage_in = !no_stage && !(host_ptr_pinned(gi) && host_ptr_pinned(vi) && (!any_mask || host_ptr_pinned(li)));
+      const bool stage_out = !no_stage && !(host_ptr_pinned(go) && host_ptr_pinned(vo));
+      if (stage_in || stage_out) kc = std::max<i64>(1, std::min<i64>(kc, (i64)(((size_t)192 << 20) / std::max<size_t>(per_field, 1))));
       IPB_CUDA(cudaStreamSynchronize(st0));        // plan ready before the second stream uses it
       size_t win_lo = 0, win_n = (size_t)mi;
       static const bool h2d_full = getenv("IPB_H2D_FULL") && atoi(getenv("IPB_H2D_FULL")) != 0;   // A/B: whole fields, plain copies
@@ -323,13 +360,19 @@ void run_on(int device, bool stats, bool vec, int dev, void* user_stream, i64 ip
                                                                  : (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
       const int nshard = (int)std::max<size_t>(1, RT.shard.size());
       const int lo_threads = std::max(1, host_threads / nshard);
+      // the staged copies of pageable arrays are plain memcpy work the call waits for: every core the shard may use
+      const int copy_threads = getenv("IPB_HOST_THREADS") ? lo_threads : std::max(lo_threads, (int)std::min(16u, std::thread::hardware_concurrency()) / nshard);
       const i64 nw = ((i64)NO + 31) / 32;
       // Everything a chunk brings back besides go sits in the slot's PINNED staging (ibo, packed lo): a device -> host copy
       // into pageable memory would hold the host until the chunk has drained, and the two chunks would never overlap.
-      struct Pending { i64 k0 = 0, kn = 0; bool on = false; const int* ints = nullptr; const unsigned* bits = nullptr; } pend[2];
+      struct Pending { i64 k0 = 0, kn = 0; bool on = false; const int* ints = nullptr; const unsigned* bits = nullptr; const R* hgo = nullptr; } pend[2];
       auto finish_chunk = [&](Pending q) {   // the chunk's stream has drained
         if (!q.on) return;
         for (i64 k = 0; k < q.kn; k++) ibo32[q.k0 + k] = q.ints[k];
+        if (q.hgo) {   // staged outputs: [kn][NO] of go, then of vo
+          copy_rows(go + (size_t)q.k0 * mo, mo * sizeof(R), q.hgo, (size_t)NO * sizeof(R), (size_t)NO * sizeof(R), (size_t)q.kn, copy_threads);
+          if (vec) copy_rows(vo + (size_t)q.k0 * mo, mo * sizeof(R), q.hgo + (size_t)q.kn * NO, (size_t)NO * sizeof(R), (size_t)NO * sizeof(R), (size_t)q.kn, copy_threads);
+        }
         if (q.bits) expand_lo(lo + (size_t)q.k0 * mo, mo, NO, q.kn, q.bits, nw, q.ints + q.kn, lo_threads);
       };
       // two staging halves per slot: the next chunk is queued on the slot BEFORE the host turns to the finished one's lo
@@ -352,7 +395,21 @@ void run_on(int device, bool stats, bool vec, int dev, void* user_stream, i64 ip
         int* d_int = (int*)w.ints.get((size_t)kn * 4 * sizeof(int));
         // only the window of the input field the plan refers to crosses PCIe (the spiral searches can leave it)
         h2d += (long long)win_n * kn * (sizeof(R) * (vec ? 2 : 1) + (any_mask ? 1 : 0));
-        if (win_lo == 0 && win_n == (size_t)mi) {
+        if (stage_in && win_n > 0) {
+          const size_t fb = (size_t)kn * win_n * sizeof(R);
+          unsigned char* h = (unsigned char*)w.hin.get(fb * (vec ? 2 : 1) + (any_mask ? (size_t)kn * win_n : 0));
+          copy_rows(h, win_n * sizeof(R), gi + (size_t)k0 * mi + win_lo, mi * sizeof(R), win_n * sizeof(R), (size_t)kn, copy_threads);
+          IPB_CUDA(cudaMemcpy2DAsync(d_gi + win_lo, mi * sizeof(R), h, win_n * sizeof(R), win_n * sizeof(R), kn, cudaMemcpyHostToDevice, s));
+          if (vec) {
+            copy_rows(h + fb, win_n * sizeof(R), vi + (size_t)k0 * mi + win_lo, mi * sizeof(R), win_n * sizeof(R), (size_t)kn, copy_threads);
+            IPB_CUDA(cudaMemcpy2DAsync(d_vi + win_lo, mi * sizeof(R), h + fb, win_n * sizeof(R), win_n * sizeof(R), kn, cudaMemcpyHostToDevice, s));
+          }
+          if (any_mask) {
+            unsigned char* hl = h + fb * (vec ? 2 : 1);
+            copy_rows(hl, win_n, li + (size_t)k0 * mi + win_lo, mi, win_n, (size_t)kn, copy_threads);
+            IPB_CUDA(cudaMemcpy2DAsync(d_li + win_lo, mi, hl, win_n, win_n, kn, cudaMemcpyHostToDevice, s));
+          }
+        } else if (win_lo == 0 && win_n == (size_t)mi) {
           IPB_CUDA(cudaMemcpyAsync(d_gi, gi + (size_t)k0 * mi, (size_t)kn * mi * sizeof(R), cudaMemcpyHostToDevice, s));
           if (vec) IPB_CUDA(cudaMemcpyAsync(d_vi, vi + (size_t)k0 * mi, (size_t)kn * mi * sizeof(R), cudaMemcpyHostToDevice, s));
           if (any_mask) IPB_CUDA(cudaMemcpyAsync(d_li, li + (size_t)k0 * mi, (size_t)kn * mi, cudaMemcpyHostToDevice, s));
@@ -388,7 +445,14 @@ void run_on(int device, bool stats, bool vec, int dev, void* user_stream, i64 ip
         }
         // only the first NO points of each field are defined (the reference leaves the rest untouched)
         d2h += (long long)NO * kn * (sizeof(R) * (vec ? 2 : 1));
-        if (NO == mo) {
+        pend[ci].hgo = nullptr;
+        if (stage_out) {
+          const size_t out_bytes = (size_t)kc * NO * sizeof(R) * (vec ? 2 : 1);   // two halves, like the small staging above
+          R* h = (R*)((unsigned char*)w.hout.get(2 * out_bytes) + ((chunk_no >> 1) & 1) * out_bytes);
+          IPB_CUDA(cudaMemcpy2DAsync(h, (size_t)NO * sizeof(R), d_go, mo * sizeof(R), (size_t)NO * sizeof(R), kn, cudaMemcpyDeviceToHost, s));
+          if (vec) IPB_CUDA(cudaMemcpy2DAsync(h + (size_t)kn * NO, (size_t)NO * sizeof(R), d_vo, mo * sizeof(R), (size_t)NO * sizeof(R), kn, cudaMemcpyDeviceToHost, s));
+          pend[ci].hgo = h;
+        } else if (NO == mo) {
           IPB_CUDA(cudaMemcpyAsync(go + (size_t)k0 * mo, d_go, (size_t)kn * mo * sizeof(R), cudaMemcpyDeviceToHost, s));
           if (vec) IPB_CUDA(cudaMemcpyAsync(vo + (size_t)k0 * mo, d_vo, (size_t)kn * mo * sizeof(R), cudaMemcpyDeviceToHost, s));
         } else {

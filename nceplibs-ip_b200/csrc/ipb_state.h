@@ -27,7 +27,7 @@ struct HBuf {  // growable pinned host staging
   void* get(size_t bytes);
   void release();
 };
-struct Work { DBuf gi, vi, li, go, vo, lo, ints, lbits; HBuf hbits; };
+struct Work { DBuf gi, vi, li, go, vo, lo, ints, lbits; HBuf hbits, hin, hout; };
 
 struct CacheEntry { std::vector<i64> key; std::shared_ptr<void> plan; int kind; size_t bytes; unsigned long long stamp; };
 

@@ -54,9 +54,20 @@ class IpLib:
         k = self._ia(desc[1], 200)
         return [_p(k)], [k]
 
-    def ipolates(self, ip, ipopt, gin, gout, mi, mo, km, ibi, li, gi, no=0, rlat=None, rlon=None, out_init=None, single=False):
+    def pinned(self, shape, dtype):
+        """numpy array over page-locked host memory from the library's allocator (ipgpu_host_alloc); kept for the process."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.lib.ipgpu_host_alloc.restype = C.c_void_p
+        self.lib.ipgpu_host_alloc.argtypes = [C.c_longlong]
+        p = self.lib.ipgpu_host_alloc(C.c_longlong(max(n, 1)))
+        if not p:
+            raise MemoryError("ipgpu_host_alloc failed")
+        return np.frombuffer((C.c_char * max(n, 1)).from_address(p), dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def ipolates(self, ip, ipopt, gin, gout, mi, mo, km, ibi, li, gi, no=0, rlat=None, rlon=None, out_init=None, single=False, pinned=False):
         """Returns dict(no, rlat, rlon, ibo, lo, go, iret).  gi: [km, mi] C-order (== Fortran GI(MI,KM)).
-        single=True calls the *_single_field entry (scalar ibi/ibo, rank-1 fields; src/ipolates.F90:158,808)."""
+        single=True calls the *_single_field entry (scalar ibi/ibo, rank-1 fields; src/ipolates.F90:158,808).
+        pinned=True puts the field arrays into page-locked memory (the library then copies them without staging)."""
         assert gin[0] == gout[0]
         assert not single or km == 1
         R = self.R
@@ -67,6 +78,10 @@ class IpLib:
         fillv = -7777.0 if out_init is None else out_init
         go = np.full((km, mo), fillv, R)
         lo = np.full((km, mo), 7, np.uint8)
+        if pinned:
+            gi_, li_, go_, lo_ = self.pinned(gi.shape, R), self.pinned(li.shape, np.uint8), self.pinned(go.shape, R), self.pinned(lo.shape, np.uint8)
+            gi_[:], li_[:], go_[:], lo_[:] = gi, li, go, lo
+            gi, li, go, lo = gi_, li_, go_, lo_
         ibo = self._ia([-7] * km)
         no_a, iret = self._ia([no]), self._ia([-7])
         a_in, keep1 = self._grid_args(gin)

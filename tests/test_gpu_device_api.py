@@ -299,12 +299,14 @@ def test_host_call_sharded_over_devices():
         assert np.array_equal(v1[k], vm[k]), k
 
 
+@pytest.mark.parametrize("pinned", [False, True])
 @pytest.mark.parametrize("kind", ["4", "d"])
 @pytest.mark.parametrize("ip", [0, 2, 3])
-def test_host_call_lo_crosses_the_link_packed(kind, ip):
+def test_host_call_lo_crosses_the_link_packed(kind, ip, pinned):
     """Host-pointer calls bring lo back as one bit per point and rebuild the caller's LOGICAL*1 array on the host
     (k_pack_lo / expand_lo): fields without a false point, fields with holes, mo > no (the tail stays untouched), a point
-    count that is no multiple of 8 or 32, and many chunks in flight one after the other."""
+    count that is no multiple of 8 or 32, and many chunks in flight one after the other.  pinned=False: ordinary (pageable)
+    arrays, which the library stages through its own page-locked buffers with host threads; True: direct copies."""
     P, O = product(kind), oracle(kind)
     gin, gout = ic.g2_input(kind), ic.g2_templates(kind)["218"]
     mi, no, km = ic.npts_of(gin), ic.npts_of(gout), 9
@@ -316,13 +318,18 @@ def test_host_call_lo_crosses_the_link_packed(kind, ip):
     ibi = [0, 1, 0, 1, 1, 0, 1, 1, 0]
     P.lib.ipgpu_set_chunk_bytes(C.c_longlong(1))   # one field per chunk
     try:
-        a = P.ipolates(ip, [-1] * 20, gin, gout, mi, mo, km, ibi, li, g)
+        a = P.ipolates(ip, [-1] * 20, gin, gout, mi, mo, km, ibi, li, g, pinned=pinned)
     finally:
         P.lib.ipgpu_set_chunk_bytes(C.c_longlong(768 << 20))
     b = O.ipolates(ip, [-1] * 20, gin, gout, mi, mo, km, ibi, li, g)
     assert a["iret"] == 0 and a["no"] == b["no"] == no
     assert np.array_equal(a["lo"], b["lo"]) and np.array_equal(a["ibo"], b["ibo"])
     assert (a["lo"][:, no:] == 7).all()          # beyond no the caller's bytes are left alone
+    assert (a["go"][:, no:] == -7777.0).all()
+    if ip != 3 or kind == "4":
+        assert np.array_equal(a["go"].view(np.uint8), b["go"].view(np.uint8))
+    else:
+        assert np.allclose(a["go"], b["go"], rtol=1e-12, atol=1e-12)
     assert a["lo"][0].min() == 1 and a["lo"][1].min() == 0
 
 
