@@ -360,6 +360,11 @@ void ipgpu_last_transfer(long long* h2d_bytes, long long* d2h_bytes); /* field b
 void* ipgpu_host_alloc(long long bytes);          /* pinned host memory on the NUMA node of the current device's PCIe link, so the host API copies asynchronously at link rate */
 void ipgpu_host_free(void* p);
 int ipgpu_device_numa_node(void);                 /* NUMA node of the current device's PCIe link, -1 unknown */
+/* host half of the host-pointer pipeline, no GPU needed (tests): what = 0 rebuilds lo (dst, pitch dpitch bytes per field, the first
+ * `width` points of each of kn fields) from packed bits (src: kn rows of ceil(width/32) words, bit i of word w = point 32 w + i) and
+ * hasfalse[kn]; what = 1 copies kn rows of `width` bytes between pitched arrays.  Returns 0. */
+int ipgpu_selftest_host(int what, int threads, unsigned char* dst, long long dpitch, const unsigned char* src, long long spitch,
+                        long long width, long long kn, const int* hasfalse);
 void ipgpu_link_probe(long long bytes, double* h2d_gbs, double* d2h_gbs, double* both_gbs); /* measured host-link ceiling (GB/s) with that allocator */
 const char* ipgpu_version(void);
 /* tile geometry of the point-staged kernels (host-side, for tests): mode 0 = 128 consecutive points, 1 = 32 x 4 patch,

@@ -27,6 +27,7 @@
 
 #include "ipb_decode.h"
 #include "ipb_state.h"
+#include "ipb_hostcopy.h"
 
 namespace ipb {
 
@@ -483,6 +484,15 @@ long long ipgpu_plan_bytes() {
 void ipgpu_set_plan_cache_bytes(long long b) { Runtime& RT = rt(); std::lock_guard<std::mutex> lock(RT.mu); RT.cache_cap = (size_t)b; }
 void ipgpu_set_chunk_bytes(long long b) { Runtime& RT = rt(); std::lock_guard<std::mutex> lock(RT.mu); RT.chunk_bytes = (size_t)std::max<long long>(b, 1 << 20); }
 long long ipgpu_launch_count() { return g_launches.load(); }
+// The host half of the host-pointer pipeline, callable without a GPU (tests -m "not gpu"): what = 0 rebuilds lo[kn][mo]
+// (first no points of each field) from bits[kn][ceil(no/32)] and hasfalse[kn]; what = 1 copies kn rows of `width` bytes
+// from src (pitch spitch) to dst (pitch dpitch).  Returns 0, or 1 for an unknown `what`.
+int ipgpu_selftest_host(int what, int threads, unsigned char* dst, long long dpitch, const unsigned char* src, long long spitch, long long width,
+                        long long kn, const int* hasfalse) {
+  if (what == 0) { expand_lo(dst, dpitch, width, kn, reinterpret_cast<const unsigned*>(src), (width + 31) / 32, hasfalse, threads); return 0; }
+  if (what == 1) { copy_rows(dst, (size_t)dpitch, src, (size_t)spitch, (size_t)width, (size_t)kn, threads); return 0; }
+  return 1;
+}
 // timings of the last ipolates/ipolatev call on this process, CUDA-event milliseconds
 void ipgpu_last_timing(double* plan_ms, double* apply_ms, int* plan_cache_hit) {
   Runtime& RT = rt();

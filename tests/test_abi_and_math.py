@@ -145,3 +145,32 @@ def test_kind_shims_export_the_reference_symbols():
         r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", f"-DLSIZE={ls}", "-I", os.path.join(ROOT, "include"), "-x", "c", "-"],
                            input=src, text=True, capture_output=True)
         assert r.returncode == 0, r.stderr
+
+
+@pytest.mark.parametrize("threads", [1, 5])
+def test_host_pipeline_helpers_without_a_gpu(threads):
+    """ipb_hostcopy.h through ipgpu_selftest_host: the caller's LOGICAL*1 array rebuilt from packed bits, and pitched row
+    copies on several host threads (what the host-pointer calls do around the device work)."""
+    lib = C.CDLL(pkg.PRODUCT_SO)
+    f = lib.ipgpu_selftest_host
+    f.restype = C.c_int
+    f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_void_p]
+    rng = np.random.default_rng(3)
+    for no, mo, kn in ((1, 1, 1), (37, 40, 3), (4099, 4100, 7), (1 << 20, (1 << 20) + 3, 9)):
+        truth = (rng.random((kn, no)) < 0.9).astype(np.uint8)
+        truth[0] = 1
+        nw = (no + 31) // 32
+        padded = np.zeros((kn, nw * 32), np.uint8)
+        padded[:, :no] = truth
+        bits = np.packbits(padded, axis=1, bitorder="little").view(np.uint32).reshape(kn, nw).copy()
+        hasfalse = (truth.min(axis=1) == 0).astype(np.int32)
+        bits[hasfalse == 0] = 0xDEADBEEF            # rows of fields without a false point are not read
+        lo = np.full((kn, mo), 7, np.uint8)
+        assert f(0, threads, lo.ctypes.data, mo, bits.ctypes.data, 0, no, kn, hasfalse.ctypes.data) == 0
+        assert np.array_equal(lo[:, :no], truth) and (lo[:, no:] == 7).all()
+    for width, sp, dp, rows in ((1, 1, 1, 1), (1000, 1024, 1000, 5), (3 << 20, (3 << 20) + 64, (3 << 20) + 8, 4), (5, 9, 7, 700000)):
+        src = rng.integers(0, 255, (rows, sp), dtype=np.uint8)
+        dst = np.full((rows, dp), 9, np.uint8)
+        assert f(1, threads, dst.ctypes.data, dp, src.ctypes.data, sp, width, rows, None) == 0
+        assert np.array_equal(dst[:, :width], src[:, :width]) and (dst[:, width:] == 9).all()
+    assert f(2, 1, None, 0, None, 0, 0, 0, None) == 1
