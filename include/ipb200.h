@@ -359,6 +359,8 @@ void ipgpu_last_timing(double* plan_ms, double* apply_ms, int* plan_cache_hit); 
 void ipgpu_last_transfer(long long* h2d_bytes, long long* d2h_bytes); /* field bytes the last host-pointer call moved over PCIe */
 void* ipgpu_host_alloc(long long bytes);          /* pinned host memory on the NUMA node of the current device's PCIe link, so the host API copies asynchronously at link rate */
 void ipgpu_host_free(void* p);
+int ipgpu_host_register(void* p, long long bytes); /* page-lock an array the caller owns (Fortran allocatable, malloc): copied directly at link rate afterwards; 0 or the cudaError */
+int ipgpu_host_unregister(void* p);
 int ipgpu_device_numa_node(void);                 /* NUMA node of the current device's PCIe link, -1 unknown */
 /* host half of the host-pointer pipeline, no GPU needed (tests): what = 0 rebuilds lo (dst, pitch dpitch bytes per field, the first
  * `width` points of each of kn fields) from packed bits (src: kn rows of ceil(width/32) words, bit i of word w = point 32 w + i) and

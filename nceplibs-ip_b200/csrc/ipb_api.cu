@@ -554,6 +554,19 @@ void ipgpu_host_free(void* p) {
   }
   cudaFreeHost(p);
 }
+// Page-lock arrays the caller already owns (a Fortran allocatable, a C malloc): host-pointer calls then copy them directly at
+// link rate instead of staging them.  Returns 0, or the cudaError (e.g. the range is registered already).
+int ipgpu_host_register(void* p, long long bytes) {
+  if (!p || bytes <= 0) return (int)cudaErrorInvalidValue;
+  const cudaError_t e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) cudaGetLastError();
+  return (int)e;
+}
+int ipgpu_host_unregister(void* p) {
+  const cudaError_t e = cudaHostUnregister(p);
+  if (e != cudaSuccess) cudaGetLastError();
+  return (int)e;
+}
 // NUMA node of the current device's PCIe link (-1 unknown)
 int ipgpu_device_numa_node() {
   int dev = 0, node = -1;

@@ -266,6 +266,23 @@ def test_pinned_allocator_and_link_probe():
     print("link GB/s h2d, d2h, both:", a.value, b.value, c.value, "numa node", lib.ipgpu_device_numa_node())
 
 
+def test_host_register_pins_a_callers_array():
+    """ipgpu_host_register: an ordinary array becomes directly copyable; results do not depend on how the arrays are held."""
+    P = product("4")
+    gin, gout = ic.g2_input("4"), ic.g2_templates("4")["218"]
+    mi, mo, km = ic.npts_of(gin), ic.npts_of(gout), 3
+    g = np.stack([ic.inputs()["snoalb"] + k for k in range(km)]).astype(np.float32)
+    a = P.ipolates(0, [-1] * 20, gin, gout, mi, mo, km, [0] * km, np.ones((km, mi), np.uint8), g)
+    assert P.lib.ipgpu_host_register(C.c_void_p(g.ctypes.data), C.c_longlong(g.nbytes)) == 0
+    try:
+        b = P.ipolates(0, [-1] * 20, gin, gout, mi, mo, km, [0] * km, np.ones((km, mi), np.uint8), g)
+    finally:
+        assert P.lib.ipgpu_host_unregister(C.c_void_p(g.ctypes.data)) == 0
+    assert P.lib.ipgpu_host_register(None, C.c_longlong(16)) != 0
+    for k in ("go", "lo", "ibo"):
+        assert np.array_equal(a[k], b[k]), k
+
+
 def test_host_call_sharded_over_devices():
     """ipgpu_set_devices(n): one host-pointer call, the field batch split over n GPUs (needs >= 2 visible devices)."""
     lib = product("4")
