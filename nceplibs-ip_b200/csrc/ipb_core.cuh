@@ -334,6 +334,7 @@ void run_on(int device, bool stats, bool vec, int dev, void* user_stream, i64 ip
       const size_t stage_bytes = (size_t)3 * kc * sizeof(int) + (lo_bytes ? 0 : (size_t)kc * nw * sizeof(unsigned));
       i64 chunk_no = 0;
       int ci = 0;
+      try {
       for (i64 k0 = 0; k0 < km; k0 += kc, ci ^= 1) {
         const i64 kn = std::min(kc, km - k0);
         cudaStream_t s = DS.stream[ci];
@@ -424,6 +425,12 @@ void run_on(int device, bool stats, bool vec, int dev, void* user_stream, i64 ip
       finish_chunk(pend[ci]);
       IPB_CUDA(cudaStreamSynchronize(DS.stream[ci ^ 1]));
       finish_chunk(pend[ci ^ 1]);
+      } catch (...) {
+        // no copy may still be writing into the caller's arrays (or reading the staging) when the error reaches the caller
+        cudaStreamSynchronize(DS.stream[0]);
+        cudaStreamSynchronize(DS.stream[1]);
+        throw;
+      }
     }
     for (i64 k = 0; k < km; k++) ibo[k] = ibo32[k];
   } else {
