@@ -296,6 +296,7 @@ void run_on(int device, bool stats, bool vec, int dev, void* user_stream, i64 ip
       const size_t per_field = ((size_t)mi + (size_t)mo) * sizeof(R) * (vec ? 2 : 1) + (any_mask ? mi : 0) + mo;
       i64 kc = std::max<i64>(1, std::min<i64>(km, (i64)(RT.chunk_bytes / std::max<size_t>(per_field, 1))));
       if (km > 1 && kc >= km) kc = (km + 1) / 2;  // at least two chunks so copies and kernels overlap
+      kc = std::min<i64>(kc, 32768);               // fields are a grid dimension of the per-chunk kernels
       // Pageable caller arrays (what a Fortran caller has) go through the slot's own pinned staging, copied by host threads:
       // left to the driver such copies run at a fraction of the link rate and hold the host, so nothing overlaps.
       static const bool no_stage = getenv("IPB_NO_STAGE") && atoi(getenv("IPB_NO_STAGE")) != 0;
