@@ -62,6 +62,7 @@ void launch_apply(const Plan<R>& P, bool vec, FieldArgs<R> a, cudaStream_t st) {
   const GridP<R>& gi = P.gin.p;
   const int method = P.method;
   if (gtiles_ok(P, a)) { launch_gtiles(P, a, st); return; }
+  if (vec && gtiles_vec_ok(P, a)) { launch_gtiles_vec(P, a, st); return; }
   if (method == M_BILINEAR || method == M_BICUBIC) {
     if (method == M_BILINEAR && !vec && box_ok(P, a) && launch_bilinear_box(P, a, st)) return;
     if (method == M_BILINEAR && !vec && tiles_ok(P, a)) { launch_bilinear_tiles(P, a, st); return; }
@@ -202,7 +203,7 @@ std::shared_ptr<Plan<R>> obtain_plan(DevState& DS, int method, bool vec, const i
     P->free_stream = DS.stream[0];
     if (P->iret == 0 && !station) { build_tile_tables<R>(*P, st); P->bytes += P->tiles.bytes; build_box_tables<R>(*P, st); }
     if (P->iret == 0) build_budget_collapse<R>(*P, st);
-    if (P->iret == 0 && !station && method != M_BILINEAR) { build_gtiles<R>(*P, st); P->bytes += P->gt.bytes; }
+    if (P->iret == 0 && !station && (method != M_BILINEAR || vec)) { build_gtiles<R>(*P, st); P->bytes += P->gt.bytes; }
     if (!station) cache_put<R>(DS, key, P);
   }
   // bilinear calls that carry a bitmap use the point-staged kernel; its tables are added to the plan on first need

@@ -40,6 +40,7 @@ namespace ipb {
 
 constexpr int GT_PTS = 128;       // output points per tile = threads per block
 constexpr int GT_MAXENT = 256;    // distinct source positions a tile may have (one-byte slots)
+constexpr int GT_MAXENT_VEC = 512; // the same for vector bilinear plans (two-byte slots: coarse output grids share few taps)
 constexpr int GT_F = 8;           // fields per staging pass
 
 __host__ __device__ inline int gt_point(const GtGeom& g, int tile, int r, int lane, int no) {
@@ -67,13 +68,13 @@ inline GtGeom gt_geom(int mode, int rowlen, int no) {
 // ---- plan time: the distinct source positions of every tile ----------------------------------------------
 // One block per tile.  write = 0: only count (maximum and total over tiles, to choose the tile shape);
 // write = 1: emit the sorted list esrc[tile][estride] (0-based, -1 = padding) and the slot of every tap.
-template <int NK>   // power of two >= 128 * U
+template <int NK, int MAXENT = GT_MAXENT>   // NK: power of two >= 128 * U; MAXENT: positions a tile's list may hold
 __global__ void __launch_bounds__(GT_PTS)
 k_gt_build(GtGeom g, int no, int U, const int* __restrict__ taps, int write, int estride, int* __restrict__ esrc,
-           u8* __restrict__ slot, int* gmax, unsigned long long* gsum, int* govf) {
+           u8* __restrict__ slot, int* gmax, unsigned long long* gsum, int* govf, unsigned short* __restrict__ slot16 = nullptr) {
   __shared__ int key[NK];
   __shared__ int part[GT_PTS + 1];
-  __shared__ int uniq[GT_MAXENT];
+  __shared__ int uniq[MAXENT];
   const int tid = threadIdx.x, tile = blockIdx.x;
   const int n = gt_point(g, tile, tid >> 5, tid & 31, no);
   for (int u = 0; u < U; u++) {
@@ -111,18 +112,18 @@ k_gt_build(GtGeom g, int no, int U, const int* __restrict__ taps, int write, int
   __syncthreads();
   const int total = part[GT_PTS];
   if (!write) {
-    if (tid == 0) { atomicMax(gmax, total); atomicAdd(gsum, (unsigned long long)total); if (total > GT_MAXENT) atomicAdd(govf, 1); }
+    if (tid == 0) { atomicMax(gmax, total); atomicAdd(gsum, (unsigned long long)total); if (total > MAXENT) atomicAdd(govf, 1); }
     return;
   }
   int pos = part[tid];
 #pragma unroll
   for (int q = 0; q < PER; q++) {
     const int i = tid * PER + q, v = key[i];
-    if (v != INT_MAX && (i == 0 || key[i - 1] != v)) { if (pos < GT_MAXENT) uniq[pos] = v; pos++; }
+    if (v != INT_MAX && (i == 0 || key[i - 1] != v)) { if (pos < MAXENT) uniq[pos] = v; pos++; }
   }
   __syncthreads();
   // a tile with more positions than the table holds is marked (-2): its points gather from global memory
-  const bool ovf = total > GT_MAXENT;
+  const bool ovf = total > MAXENT;
   const int ne = ovf ? 0 : total;
   for (int i = tid; i < estride; i += GT_PTS) esrc[(size_t)tile * estride + i] = i < ne ? uniq[i] : (ovf && i == 0 ? -2 : -1);
   if (n < 0) return;
@@ -134,7 +135,7 @@ k_gt_build(GtGeom g, int no, int U, const int* __restrict__ taps, int write, int
       while (lo < hi) { const int mid = (lo + hi) >> 1; if (uniq[mid] < p - 1) lo = mid + 1; else hi = mid; }
       s = lo;
     }
-    slot[(size_t)u * no + n] = (u8)s;
+    if (slot16) slot16[(size_t)u * no + n] = (unsigned short)s; else slot[(size_t)u * no + n] = (u8)s;
   }
 }
 
@@ -142,10 +143,15 @@ template <class R> void build_gtiles(Plan<R>& P, cudaStream_t st) {
   GtTables& T = P.gt;
   T = GtTables();
   static const bool off = getenv("IPB_NO_GTILES") && atoi(getenv("IPB_NO_GTILES")) != 0;
-  if (off || P.vec || P.no <= 0) return;
+  if (off || P.no <= 0) return;
   const int* taps = nullptr;
   int U = 0;
-  if (P.method == M_BICUBIC && P.nxy) { taps = P.nxy; U = 16; }
+  const bool vecb = P.vec && P.method == M_BILINEAR && P.nxy;   // vector bilinear: lists of up to 512 positions, 16-bit slots (k_gtiles_vec)
+  static const bool vec_off = getenv("IPB_NO_GTILES_VEC") && atoi(getenv("IPB_NO_GTILES_VEC")) != 0;
+  if (P.vec && (!vecb || vec_off)) return;
+  const int maxent = vecb ? GT_MAXENT_VEC : GT_MAXENT;
+  if (vecb) { taps = P.nxy; U = 4; }
+  else if (P.method == M_BICUBIC && P.nxy) { taps = P.nxy; U = 16; }
   else if (P.method == M_BILINEAR && P.nxy) { taps = P.nxy; U = 4; }   // built on demand (first call with a bitmap): run()
   else if (P.method == M_BUDGET && P.cu > 0 && P.cn) { taps = P.cn; U = P.cu; }
   else return;
@@ -160,7 +166,8 @@ template <class R> void build_gtiles(Plan<R>& P, cudaStream_t st) {
   IPB_CUDA(cudaMemsetAsync(d_max, 0, 8 * sizeof(int), st));
   IPB_CUDA(cudaMemsetAsync(d_sum, 0, 4 * sizeof(unsigned long long), st));
   auto launch = [&](const GtGeom& g, int write, int estride, int m) {
-    if (U == 1) k_gt_build<128><<<g.ntile, GT_PTS, 0, st>>>(g, no, U, taps, write, estride, T.esrc, T.slot, d_max + m, d_sum + m, d_ovf + m);
+    if (vecb) k_gt_build<512, GT_MAXENT_VEC><<<g.ntile, GT_PTS, 0, st>>>(g, no, U, taps, write, estride, T.esrc, nullptr, d_max + m, d_sum + m, d_ovf + m, T.slot16);
+    else if (U == 1) k_gt_build<128><<<g.ntile, GT_PTS, 0, st>>>(g, no, U, taps, write, estride, T.esrc, T.slot, d_max + m, d_sum + m, d_ovf + m);
     else if (U <= 4) k_gt_build<512><<<g.ntile, GT_PTS, 0, st>>>(g, no, U, taps, write, estride, T.esrc, T.slot, d_max + m, d_sum + m, d_ovf + m);
     else k_gt_build<2048><<<g.ntile, GT_PTS, 0, st>>>(g, no, U, taps, write, estride, T.esrc, T.slot, d_max + m, d_sum + m, d_ovf + m);
     g_launches++;
@@ -175,7 +182,7 @@ template <class R> void build_gtiles(Plan<R>& P, cudaStream_t st) {
   if (getenv("IPB_DEBUG"))
     for (int m = 0; m < nmode; m++)
       fprintf(stderr, "ipb200: gtiles method %d U %d mode %d: tiles %d, max %d, mean %.1f distinct positions per tile, %d tiles over %d\n", P.method, U, m,
-              gt_geom(m, rowlen, no).ntile, hmax[m], (double)hsum[m] / gt_geom(m, rowlen, no).ntile, hovf[m], GT_MAXENT);
+              gt_geom(m, rowlen, no).ntile, hmax[m], (double)hsum[m] / gt_geom(m, rowlen, no).ntile, hovf[m], maxent);
   // Tile shape: fewest staging copies per field, where a tile whose list does not fit (it gathers from global
   // memory) counts like 2048 copies and the 16x8 patch pays for its short store runs (two 16-point runs per
   // warp instruction instead of one 32-point run).  Measured on the BASELINE pairs: profiles/README.md.
@@ -186,7 +193,7 @@ template <class R> void build_gtiles(Plan<R>& P, cudaStream_t st) {
     if (hmax[m] <= 0) continue;
     const int nt = gt_geom(m, rowlen, no).ntile;
     // only the bicubic kernel has a per-tile fallback for lists that do not fit
-    if (hmax[m] > GT_MAXENT && !(P.method == M_BICUBIC && hovf[m] <= nt / 8)) continue;
+    if (hmax[m] > maxent && !((P.method == M_BICUBIC || vecb) && hovf[m] <= nt / 8)) continue;
     if (force >= 0 && m != force) continue;
     const double cost = (double)hsum[m] + 2048.0 * hovf[m] + (m == 2 ? 64.0 * nt : 0.0);
     if (best < 0 || cost < best_cost) { best = m; best_cost = cost; }
@@ -195,13 +202,13 @@ template <class R> void build_gtiles(Plan<R>& P, cudaStream_t st) {
     T.geom = gt_geom(best, rowlen, no);
     T.U = U;
     T.maxent = hmax[best];
-    T.estride = hmax[best] <= GT_PTS ? GT_PTS : 2 * GT_PTS;
+    T.estride = vecb ? GT_PTS * std::min(4, std::max(1, (std::min(hmax[best], maxent) + GT_PTS - 1) / GT_PTS)) : (hmax[best] <= GT_PTS ? GT_PTS : 2 * GT_PTS);
     T.novf = hovf[best];
     T.esrc = dalloc<int>((size_t)T.geom.ntile * T.estride);
-    T.slot = dalloc<u8>((size_t)U * no);
+    if (vecb) T.slot16 = dalloc<unsigned short>((size_t)U * no); else T.slot = dalloc<u8>((size_t)U * no);
     launch(T.geom, 1, T.estride, 3);
     T.entries = hsum[best];
-    T.bytes = (size_t)T.geom.ntile * T.estride * 4 + (size_t)U * no;
+    T.bytes = (size_t)T.geom.ntile * T.estride * 4 + (size_t)U * no * (vecb ? 2 : 1);
     T.ok = true;
   }
   dfree(d_max); dfree(d_sum);
@@ -272,6 +279,11 @@ template <class R, int IMM> __device__ __forceinline__ R lds_at(unsigned addr) {
   else asm("ld.shared.f64 %0, [%1+%2];" : "=d"(*reinterpret_cast<double*>(&v)) : "r"(addr), "n"(IMM));
   return v;
 }
+// two adjacent values (the u and v of one staged position) with one shared-memory load
+template <class R, int IMM> __device__ __forceinline__ void lds2_at(unsigned addr, R& x, R& y) {
+  if (sizeof(R) == 4) asm("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(*reinterpret_cast<float*>(&x)), "=f"(*reinterpret_cast<float*>(&y)) : "r"(addr), "n"(IMM));
+  else asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(*reinterpret_cast<double*>(&x)), "=d"(*reinterpret_cast<double*>(&y)) : "r"(addr), "n"(IMM));
+}
 __device__ __forceinline__ unsigned pass_token() { unsigned t; asm volatile("mov.u32 %0, 0;" : "=r"(t) :: "memory"); return t; }
 
 template <class Fn, int... I> __device__ __forceinline__ void static_for_impl(Fn&& fn, std::integer_sequence<int, I...>) { (fn(std::integral_constant<int, I>{}), ...); }
@@ -302,10 +314,11 @@ constexpr int GT_MAXKPB = 256;   // fields per block at most (bitmap flags of th
 #ifndef IPB_GT_MINB_BUDGET
 #define IPB_GT_MINB_BUDGET 4
 #endif
-template <class R, int U, int KIND, int NE, bool MASKED>
-__global__ void __launch_bounds__(GT_PTS, KIND == GT_BUDGET ? IPB_GT_MINB_BUDGET : (sizeof(R) == 4 ? 5 : 4))
+template <class R, int U, int KIND, int NE, bool MASKED, int FP = GT_F, int MB = 0>   // FP < 8 only without bitmaps (the usable-tap bytes hold 8 fields)
+__global__ void __launch_bounds__(GT_PTS, MB > 0 ? MB : (KIND == GT_BUDGET ? IPB_GT_MINB_BUDGET : (sizeof(R) == 4 ? 5 : 4)))
 k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
-  constexpr int F = GT_F, ESTR = GT_PTS * NE, BUF = F * ESTR;
+  static_assert(FP == 8 || !MASKED, "bitmap passes are 8 fields wide");
+  constexpr int F = FP, ESTR = GT_PTS * NE, BUF = F * ESTR;
   constexpr int NW = (U + 3) / 4;
   constexpr bool SUMK = KIND == GT_BUDGET || KIND == GT_BILIN;   // weighted sum over the usable taps, bitmaps from shared memory
   constexpr bool EXACT = KIND == GT_BILIN;                        // bit-exact contract: IEEE division by the weight sum in tap order
@@ -694,6 +707,208 @@ k_gtiles(FieldArgs<R> a, GtArgs<R> T, int kpb) {
 }
 
 
+// ---- vector bilinear (ipolatev ip = 0; bilinear_interp_mod.F90:463-546): both wind components point-staged -------------
+// The same scheme for field pairs: u and v at the tile's distinct source positions go to shared memory once per pass, every
+// point reads its four taps of both from there, rotates them tap by tap (cxy, sxy from movect), sums in the reference's
+// order, rotates to the output grid (crot, srot) and divides by the weight sum — k_apply_stencil<2, true>'s arithmetic,
+// bit for bit.  Output grids coarser than the input share few taps (NH polar stereographic 512 x 512 from 0.25 degrees: 232
+// distinct positions per 128-point tile on average, 512 at the most), hence lists of up to 512 positions and two-byte
+// slots; what is gained is the address-sorted staging: a handful of sectors per warp instruction instead of twenty.
+// Batches with bitmaps and points with an incomplete stencil take the general per-point code.
+// Fields per pass and resident blocks per SM, measured on BASELINE config 4 (S -> NH polar stereographic, km = 512 pairs;
+// profiles/README.md): 8 / 4 / 2 / 1 pairs per pass with 3 / 4 / 7 / 8 blocks -> 1.21 / 1.18 / 0.93 / 1.08 ms.  Short passes
+// keep the staging of one block from holding the load queue of the SM (ncu on the 4-pair form: mio_throttle 2.8 per issue).
+constexpr int GT_VEC_F = 2;
+template <class R> struct GtVecB { static constexpr int v = sizeof(R) == 4 ? 7 : 4; };
+
+template <class R, int NE, int F = GT_VEC_F, int MINB = GtVecB<R>::v>   // F: field pairs per pass
+__global__ void __launch_bounds__(GT_PTS, MINB)
+k_gtiles_vec(FieldArgs<R> a, GtGeom g, int estride, const int* __restrict__ esrc, const unsigned short* __restrict__ slot16,
+             const int* __restrict__ nxy, const R* __restrict__ wxy, const R* __restrict__ cxy, const R* __restrict__ sxy,
+             const R* __restrict__ crot, const R* __restrict__ srot, int kpb) {
+  constexpr int ESTR = GT_PTS * NE, COMP = F * ESTR, BUF = 2 * COMP;
+  extern __shared__ __align__(16) unsigned char gt_sm[];
+  R* sm = reinterpret_cast<R*>(gt_sm);                    // [2 buffers][F][ESTR][u, v]: one load brings both components of a tap
+  const int tid = threadIdx.x, r = tid >> 5, lane = tid & 31, tile = blockIdx.x;
+  const int k0 = blockIdx.y * kpb, k1 = min(k0 + kpb, a.kc);
+  if (k0 >= k1) return;
+  const int no = a.no;
+  const int n = gt_point(g, tile, r, lane, no);
+  const bool live = n >= 0;
+  const size_t nn = live ? (size_t)n : 0;
+  const size_t mi = (size_t)a.mi;
+  const int* __restrict__ es = esrc + (size_t)tile * estride;
+  int src[NE];
+  bool act[NE];
+#pragma unroll
+  for (int i = 0; i < NE; i++) {
+    const int s = es[tid + GT_PTS * i];
+    act[i] = s >= 0;
+    src[i] = act[i] ? s : 0;
+  }
+  const unsigned sm_base = (unsigned)__cvta_generic_to_shared(sm);
+  auto stage = [&](int buf, int kb) {
+    const int nf = min(F, k1 - kb);
+#pragma unroll
+    for (int i = 0; i < NE; i++) {
+      if (act[i]) {
+        const R* __restrict__ gp = a.gi + (size_t)kb * mi + src[i];
+        const R* __restrict__ vp = a.vi + (size_t)kb * mi + src[i];
+        const unsigned d = sm_base + (unsigned)((buf * BUF + 2 * (tid + GT_PTS * i)) * sizeof(R));
+        if (nf == F) {
+#pragma unroll
+          for (int f = 0; f < F; f++) {
+            cp_async_b<sizeof(R)>(d + (unsigned)(2 * f * ESTR * sizeof(R)), gp + (size_t)f * mi);
+            cp_async_b<sizeof(R)>(d + (unsigned)((2 * f * ESTR + 1) * sizeof(R)), vp + (size_t)f * mi);
+          }
+        } else {
+          for (int f = 0; f < nf; f++) {
+            cp_async_b<sizeof(R)>(d + (unsigned)(2 * f * ESTR * sizeof(R)), gp + (size_t)f * mi);
+            cp_async_b<sizeof(R)>(d + (unsigned)((2 * f * ESTR + 1) * sizeof(R)), vp + (size_t)f * mi);
+          }
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  // ---- per-point plan data, every load issued before any is consumed ----
+  R w[4], c[4], s[4];
+  int idx[4];
+  unsigned soff[4];
+  {
+    unsigned short sl[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) sl[t] = __ldg(slot16 + (size_t)t * no + nn);
+#pragma unroll
+    for (int t = 0; t < 4; t++) { idx[t] = __ldg(nxy + (size_t)t * no + nn); w[t] = __ldg(wxy + (size_t)t * no + nn); }
+#pragma unroll
+    for (int t = 0; t < 4; t++) { c[t] = __ldg(cxy + (size_t)t * no + nn); s[t] = __ldg(sxy + (size_t)t * no + nn); }
+#pragma unroll
+    for (int t = 0; t < 4; t++) soff[t] = sm_base + (live ? (unsigned)sl[t] : 0u) * (unsigned)(2 * sizeof(R));
+  }
+  const R cr = __ldg(crot + nn), sr = __ldg(srot + nn);
+  bool complete = live;
+  R Wall = 0;
+#pragma unroll
+  for (int t = 0; t < 4; t++) { complete = complete && idx[t] > 0; Wall = Wall + w[t]; }
+  complete = complete && Wall >= a.pmp;
+  R* go = a.go + (size_t)k0 * a.mo + nn;
+  R* vo = a.vo + (size_t)k0 * a.mo + nn;
+  u8* lo = a.lo + (size_t)k0 * a.mo + nn;
+  stage(0, k0);
+  int buf = 0;
+  for (int kb = k0; kb < k1; kb += F) {
+    const bool more = kb + F < k1;
+    if (more) stage(buf ^ 1, kb + F);
+    else asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    __syncthreads();
+    {
+      const unsigned tok = pass_token() + (kb == k0 ? 0u : (buf ? (unsigned)(BUF * sizeof(R)) : 0u - (unsigned)(BUF * sizeof(R))));
+#pragma unroll
+      for (int t = 0; t < 4; t++) soff[t] += tok;
+    }
+    const int nf = min(F, k1 - kb);
+    const bool fast = nf == F && __all_sync(0xffffffffu, complete || !live);
+    if (fast) {
+      static_for<F>([&](auto fc) {
+        constexpr int f = decltype(fc)::value;
+        R u[4], v[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) lds2_at<R, 2 * f * ESTR * (int)sizeof(R)>(soff[t], u[t], v[t]);
+        R G = 0, V = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          const R ur = c[t] * u[t] - s[t] * v[t];
+          const R vr = s[t] * u[t] + c[t] * v[t];
+          G = G + w[t] * ur;
+          V = V + w[t] * vr;
+        }
+        const R ur = cr * G - sr * V;
+        const R vr = sr * G + cr * V;
+        if (live) { __stcs(go, ur / Wall); __stcs(vo, vr / Wall); __stcs(lo, (u8)1); }
+        go += a.mo; vo += a.mo; lo += a.mo;
+      });
+    } else {
+#pragma unroll 1
+      for (int f = 0; f < nf; f++) {
+        const int k = kb + f;
+        R og = 0, ov = 0;
+        bool good = false;
+        if (complete) {
+          const unsigned fo = (unsigned)(2 * f * ESTR * sizeof(R));
+          R G = 0, V = 0;
+#pragma unroll
+          for (int t = 0; t < 4; t++) {
+            R u, v;
+            lds2_at<R, 0>(soff[t] + fo, u, v);
+            const R ur = c[t] * u - s[t] * v;
+            const R vr = s[t] * u + c[t] * v;
+            G = G + w[t] * ur;
+            V = V + w[t] * vr;
+          }
+          const R ur = cr * G - sr * V;
+          const R vr = sr * G + cr * V;
+          og = ur / Wall; ov = vr / Wall;
+          good = true;
+        } else if (live) {   // a tap outside the input grid: the reference's loop body from global memory
+          const R* __restrict__ gk = a.gi + (size_t)k * mi;
+          const R* __restrict__ vk = a.vi + (size_t)k * mi;
+          R G = 0, V = 0, W = 0;
+#pragma unroll
+          for (int t = 0; t < 4; t++) {
+            const int p = idx[t];
+            if (p > 0) {
+              const R u = gk[p - 1], v = vk[p - 1];
+              const R ur = c[t] * u - s[t] * v;
+              const R vr = s[t] * u + c[t] * v;
+              G = G + w[t] * ur;
+              V = V + w[t] * vr;
+              W = W + w[t];
+            }
+          }
+          good = W >= a.pmp;
+          if (good) {
+            const R ur = cr * G - sr * V;
+            const R vr = sr * G + cr * V;
+            og = ur / W; ov = vr / W;
+          }
+        }
+        if (live) {
+          __stcs(go, og); __stcs(vo, ov); __stcs(lo, (u8)(good ? 1 : 0));
+          if (!good) mark_bad(a.flag, k);
+        }
+        go += a.mo; vo += a.mo; lo += a.mo;
+      }
+    }
+    __syncthreads();
+    buf ^= 1;
+  }
+}
+
+template <class R> bool gtiles_vec_ok(const Plan<R>& P, const FieldArgs<R>& a) {
+  return P.gt.ok && P.vec && P.method == M_BILINEAR && P.gt.slot16 != nullptr && P.gt.novf == 0 && a.li == nullptr && a.vi != nullptr && a.vo != nullptr;
+}
+template <class R, int NE> void launch_gtiles_vec_inst(const Plan<R>& P, const FieldArgs<R>& a, int kpb, cudaStream_t st) {
+  constexpr int ESTR = GT_PTS * NE, F = GT_VEC_F;
+  constexpr int SM = 2 * 2 * F * ESTR * (int)sizeof(R);
+  static_assert(SM <= 48 * 1024, "fits the default dynamic shared-memory limit");
+  const GtTables& G = P.gt;
+  dim3 grid(G.geom.ntile, nblk(a.kc, kpb));
+  k_gtiles_vec<R, NE><<<grid, GT_PTS, SM, st>>>(a, G.geom, G.estride, G.esrc, G.slot16, P.nxy, P.wxy, P.cxy, P.sxy, P.crot, P.srot, kpb);
+}
+template <class R> void launch_gtiles_vec(const Plan<R>& P, const FieldArgs<R>& a, cudaStream_t st) {
+  static const int kpb_env = getenv("IPB_GKPB") ? atoi(getenv("IPB_GKPB")) : 0;
+  const int kpb = std::max(8, std::min(GT_MAXKPB, (std::min(a.kc, kpb_env > 0 ? kpb_env : 64) + 7) / 8 * 8));   // (fields per block: the point's plan data is re-read once per kpb pairs)
+  switch (P.gt.estride / GT_PTS) {
+    case 1: launch_gtiles_vec_inst<R, 1>(P, a, kpb, st); break;
+    case 2: launch_gtiles_vec_inst<R, 2>(P, a, kpb, st); break;
+    case 3: launch_gtiles_vec_inst<R, 3>(P, a, kpb, st); break;
+    default: launch_gtiles_vec_inst<R, 4>(P, a, kpb, st); break;
+  }
+  g_launches++;
+}
+
 template <class R> bool gtiles_ok(const Plan<R>& P, const FieldArgs<R>& a) {
   if (!P.gt.ok || P.vec) return false;
   if (P.method == M_BICUBIC) return true;
@@ -702,17 +917,18 @@ template <class R> bool gtiles_ok(const Plan<R>& P, const FieldArgs<R>& a) {
   return false;
 }
 
-template <class R, int U, int KIND, int NE, bool MASKED>
+template <class R, int U, int KIND, int NE, bool MASKED, int FP = GT_F, int MB = 0>
 void launch_gtiles_inst(const FieldArgs<R>& a, const GtArgs<R>& T, int kpb, cudaStream_t st) {
-  constexpr int SM = 2 * GT_F * GT_PTS * NE * (int)sizeof(R) + (MASKED ? GT_PTS * NE : 0);
+  constexpr int SM = 2 * FP * GT_PTS * NE * (int)sizeof(R) + (MASKED ? GT_PTS * NE : 0);
   static_assert(SM <= 48 * 1024, "fits the default dynamic shared-memory limit: no per-device function attribute needed");
   dim3 grid(T.g.ntile, nblk(a.kc, kpb));
-  k_gtiles<R, U, KIND, NE, MASKED><<<grid, GT_PTS, SM, st>>>(a, T, kpb);
+  k_gtiles<R, U, KIND, NE, MASKED, FP, MB><<<grid, GT_PTS, SM, st>>>(a, T, kpb);
 }
 template <class R, int U, int KIND>
 void launch_gtiles_u(const FieldArgs<R>& a, const GtArgs<R>& T, int kpb, bool masked, cudaStream_t st) {
   const bool two = T.estride > GT_PTS;
   if constexpr (KIND == GT_STENCIL) {   // bicubic bitmap fields take the general per-point path: no staged bitmap
+    // (4 or 2 fields per pass with 5-7 resident blocks, the vector kernel's recipe, lose here: 4.50-7.15 ms against 4.37)
     if (two) launch_gtiles_inst<R, U, KIND, 2, false>(a, T, kpb, st); else launch_gtiles_inst<R, U, KIND, 1, false>(a, T, kpb, st);
   } else {
     if (two) { if (masked) launch_gtiles_inst<R, U, KIND, 2, true>(a, T, kpb, st); else launch_gtiles_inst<R, U, KIND, 2, false>(a, T, kpb, st); }

@@ -90,6 +90,7 @@ struct GtTables {
   unsigned long long entries = 0;   // distinct positions summed over tiles (= staging copies per field)
   int* esrc = nullptr;              // [ntile][estride] sorted 0-based source positions, -1 = padding
   u8* slot = nullptr;               // [U][no] position of every tap in its tile's list
+  unsigned short* slot16 = nullptr; // the same for lists of up to 512 positions (vector bilinear)
   size_t bytes = 0;
 };
 struct TileDev { const u8* cid[4]; const int* ncell[4]; const int* cells[4]; const u8* edst[4]; int cstride; int ntile; };
@@ -144,7 +145,7 @@ template <class R> struct Plan {
     dfree(pole_n); dfree(pole_s); dfree(pclon_n); dfree(pslon_n); dfree(pclon_s); dfree(pslon_s);
     for (int v = 0; v < 4; v++) { dfree(tiles.cid[v]); dfree(tiles.ncell[v]); dfree(tiles.cells[v]); dfree(tiles.edst[v]); }
     dfree(wq); dfree(ws2); dfree(bxy);
-    dfree(gt.esrc); dfree(gt.slot);
+    dfree(gt.esrc); dfree(gt.slot); dfree(gt.slot16);
   }
 };
 
