@@ -406,7 +406,7 @@ template <> __device__ __forceinline__ void add2_if<float>(unsigned on, float& a
 // per 8.  Accumulation order and association are the reference's: per sample either the 4-tap sum times the
 // sample weight (field without bitmap) or tap by tap with the product wb*w formed first (field with bitmap).
 template <class R, int KF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_budget_scalar(FieldArgs<R> a, int nsamp, const int* __restrict__ bn, const R* __restrict__ bw, const R* __restrict__ wbs) {
   constexpr int SCH = 16;                              // samples per shared-memory chunk
   __shared__ int s_idx[SCH * 4 * 32];
@@ -424,6 +424,11 @@ k_budget_scalar(FieldArgs<R> a, int nsamp, const int* __restrict__ bn, const R* 
     if (k0 + f < a.kc && a.ibi[k0 + f] != 0) maskbits |= 1u << f;
   }
   R wo_plain = 0;                                      // weight sum of the fields without a bitmap (the same for all of them)
+  // element offset of every field of this warp, formed once (the launcher checks that kc * mi fits 32 bits): the kernel is
+  // bound by instruction issue, and a 64-bit k * mi per gather was a good part of it
+  unsigned koff[KF];
+#pragma unroll
+  for (int f = 0; f < KF; f++) koff[f] = (unsigned)min(k0 + f, a.kc - 1) * (unsigned)a.mi;
   for (int s0 = 0; s0 < nsamp; s0 += SCH) {
     const int ns = min(SCH, nsamp - s0);
     __syncthreads();
@@ -445,17 +450,19 @@ k_budget_scalar(FieldArgs<R> a, int nsamp, const int* __restrict__ bn, const R* 
       const R b0 = wb * w0, b1 = wb * w1, b2 = wb * w2, b3 = wb * w3;   // WB*W11 ... formed first, as the reference's left-to-right product
       wo_plain = wo_plain + wb;
 #pragma unroll
+      const unsigned j0 = (unsigned)(i0 - 1), j1 = (unsigned)(i1 - 1), j2 = (unsigned)(i2 - 1), j3 = (unsigned)(i3 - 1);
+#pragma unroll
       for (int f = 0; f < KF; f++) {
-        const int k = min(k0 + f, a.kc - 1);
-        const R* __restrict__ g = a.gi + (size_t)k * a.mi;
+        const R* __restrict__ g = a.gi;
+        const unsigned o = koff[f];
         if (!((maskbits >> f) & 1u)) {
-          const R gb = w0 * __ldg(g + (i0 - 1)) + w1 * __ldg(g + (i1 - 1)) + w2 * __ldg(g + (i2 - 1)) + w3 * __ldg(g + (i3 - 1));
+          const R gb = w0 * __ldg(g + (o + j0)) + w1 * __ldg(g + (o + j1)) + w2 * __ldg(g + (o + j2)) + w3 * __ldg(g + (o + j3));
           acc[f] = acc[f] + wb * gb;
         } else {
           // straight-line: every tap is loaded (the positions are valid), the bitmap only predicates the adds
-          const u8* __restrict__ l = a.li + (size_t)k * a.mi;
-          const u8 l0 = __ldg(l + (i0 - 1)), l1 = __ldg(l + (i1 - 1)), l2 = __ldg(l + (i2 - 1)), l3 = __ldg(l + (i3 - 1));
-          const R g0 = __ldg(g + (i0 - 1)), g1 = __ldg(g + (i1 - 1)), g2 = __ldg(g + (i2 - 1)), g3 = __ldg(g + (i3 - 1));
+          const u8* __restrict__ l = a.li;
+          const u8 l0 = __ldg(l + (o + j0)), l1 = __ldg(l + (o + j1)), l2 = __ldg(l + (o + j2)), l3 = __ldg(l + (o + j3));
+          const R g0 = __ldg(g + (o + j0)), g1 = __ldg(g + (o + j1)), g2 = __ldg(g + (o + j2)), g3 = __ldg(g + (o + j3));
           R ac = acc[f], wc = wo[f];
           add2_if<R>(l0, ac, b0 * g0, wc, b0);
           add2_if<R>(l1, ac, b1 * g1, wc, b1);

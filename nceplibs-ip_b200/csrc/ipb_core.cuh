@@ -91,7 +91,7 @@ void launch_apply(const Plan<R>& P, bool vec, FieldArgs<R> a, cudaStream_t st) {
     dim3 grid(nblk(no, 128), nblk(a.kc, KF));
     const int ns = P.bo.nsamp;
     if (budget_collapsed_ok(P, a)) { launch_budget_collapsed(P, a, st); return; }
-    if (method == M_BUDGET && !vec && a.mspiral <= 1 && ns > 0) {
+    if (method == M_BUDGET && !vec && a.mspiral <= 1 && ns > 0 && (size_t)a.kc * (size_t)a.mi < ((size_t)1 << 32)) {   // 32-bit element offsets inside
       k_budget_scalar<R, KF><<<dim3(nblk(no, 32), nblk(a.kc, 8 * KF)), 256, 0, st>>>(a, ns, P.bn, P.bw, P.d_wb);
       g_launches++;
       return;
