@@ -129,6 +129,21 @@ def test_fortran_shim_fits_free_form_line_limit(lsize):
     assert not missing, missing
 
 
+def test_fortran_management_module_matches_the_library():
+    """fortran/ipb200_gpu.F90 (interfaces of the ipgpu_* management entry points): free-form line limit, every bind(c) name
+    exported by the library and declared in include/ipb200.h."""
+    src = open(os.path.join(ROOT, "fortran", "ipb200_gpu.F90")).read()
+    code = [ln for ln in src.splitlines() if ln.strip() and not ln.lstrip().startswith("!")]
+    assert max(len(ln) for ln in code) <= 132
+    names = re.findall(r"bind\(c,\s*name='([a-z0-9_]+)'\)", src)
+    assert len(names) >= 12 and len(set(names)) == len(names)
+    lib = C.CDLL(pkg.PRODUCT_SO)
+    declared = set(_declared_symbols())
+    for n in names:
+        assert hasattr(lib, n), n
+        assert n in declared, n
+
+
 def test_kind_shims_export_the_reference_symbols():
     """libip_4 / libip_d / libip_8 (shims/ip_shim.c): the unsuffixed names the reference's libraries export, for C callers."""
     pkg.build_library()
