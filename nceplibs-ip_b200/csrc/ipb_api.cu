@@ -467,6 +467,7 @@ void ipgpu_plan_clear() {
     DeviceGuard guard(d->device);
     d->cache.clear();
     for (int i = 0; i < 2; i++) { Work& w = d->work[i]; w.gi.release(); w.vi.release(); w.li.release(); w.go.release(); w.vo.release(); w.lo.release(); w.ints.release(); w.lbits.release(); w.hbits.release(); w.hin.release(); w.hout.release(); }
+    d->geo.release();
   }
 }
 long long ipgpu_plan_count() {

@@ -249,17 +249,30 @@ void run_on(int device, bool stats, bool vec, int dev, void* user_stream, i64 ip
   // lat/lon (and rotations) are outputs for real grids; for stations the budget-family vector
   // routines overwrite crot/srot (see k_out_geo)
   // (in the device-pointer entry points these four are device arrays, or null to skip the copy)
+  // A pageable destination would hold the host for the length of the copy (and of whatever is queued before it): such
+  // arrays are filled from a pinned staging buffer once the stream has drained (finish_geo).
+  struct GeoLate { void* dst; const void* src; size_t bytes; };
+  std::vector<GeoLate> geo_late;
   auto copy_geo = [&](cudaStream_t s) {
     if (mo <= 0) return;
-    if (!station) {
-      if (rlat) IPB_CUDA(cudaMemcpyAsync(rlat, P->rlat, mo * sizeof(R), cudaMemcpyDefault, s));
-      if (rlon) IPB_CUDA(cudaMemcpyAsync(rlon, P->rlon, mo * sizeof(R), cudaMemcpyDefault, s));
-    }
-    if (vec && (!station || budget)) {
-      if (crot) IPB_CUDA(cudaMemcpyAsync(crot, P->crot, mo * sizeof(R), cudaMemcpyDefault, s));
-      if (srot) IPB_CUDA(cudaMemcpyAsync(srot, P->srot, mo * sizeof(R), cudaMemcpyDefault, s));
-    }
+    const size_t nb = (size_t)mo * sizeof(R);
+    unsigned char* stage = nullptr;
+    int used = 0;
+    auto one = [&](R* dst, const R* src) {
+      if (!dst) return;
+      if (!dev && !host_ptr_pinned(dst)) {
+        if (!stage) stage = (unsigned char*)DS.geo.get(4 * nb);
+        IPB_CUDA(cudaMemcpyAsync(stage + used * nb, src, nb, cudaMemcpyDeviceToHost, s));
+        geo_late.push_back({dst, stage + used * nb, nb});
+        used++;
+      } else {
+        IPB_CUDA(cudaMemcpyAsync(dst, src, nb, cudaMemcpyDefault, s));
+      }
+    };
+    if (!station) { one(rlat, P->rlat); one(rlon, P->rlon); }
+    if (vec && (!station || budget)) { one(crot, P->crot); one(srot, P->srot); }
   };
+  auto finish_geo = [&]() { for (const GeoLate& g : geo_late) memcpy(g.dst, g.src, g.bytes); geo_late.clear(); };
   if (budget) {
     // the budget family has no early exit: with bad options it still runs its finish loop
     // (budget_interp_mod.F90:178-181,288-344)
@@ -270,6 +283,7 @@ void run_on(int device, bool stats, bool vec, int dev, void* user_stream, i64 ip
     iret = P->iret;
     copy_geo(st0);
     IPB_CUDA(cudaStreamSynchronize(st0));
+    finish_geo();
     if (!station) no = 0;
     return;
   } else {
@@ -439,6 +453,7 @@ void run_on(int device, bool stats, bool vec, int dev, void* user_stream, i64 ip
     IPB_CUDA(cudaStreamSynchronize(st0));
     for (i64 k = 0; k < km; k++) ibo[k] = ibi[k];
   }
+  finish_geo();   // every branch above has drained st0
   cudaEventRecord(DS.ev[2], st0);
   cudaEventSynchronize(DS.ev[2]);
   if (stats) {

@@ -44,6 +44,7 @@ struct DevState {
   cudaStream_t stream[2] = {nullptr, nullptr};
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // timing events, reused by every call
   Work work[2];
+  HBuf geo;                              // pinned staging of rlat / rlon / crot / srot for callers with pageable arrays
   std::vector<CacheEntry> cache;
   unsigned long long stamp = 0;
 };
