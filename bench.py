@@ -152,7 +152,11 @@ class ClockSampler:
             r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
         bits = [getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8), getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
                 getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20), getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)]
-        return [time.perf_counter(), float(sm), float(mx), float(pw)] + [bool(r & b) for b in bits]
+        try:
+            mem = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_MEM))
+        except Exception:
+            mem = None
+        return [time.perf_counter(), float(sm), float(mx), float(pw)] + [bool(r & b) for b in bits] + [mem]
 
     def _sample_smi(self):
         o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
@@ -194,6 +198,11 @@ class ClockSampler:
         if inside:
             smi = sorted(r[1] for r in inside)
             out["sm_mhz_timed_region"] = smi[len(smi) // 2]
+        mem = [r[8] for r in (inside or load) if len(r) > 8 and r[8] is not None]
+        if mem:   # the HBM clock next to the SM clock: this path is bound by memory, not by the SMs
+            out["mem_mhz_min"], out["mem_mhz_max"] = min(mem), max(mem)
+            pw = [r[3] for r in (inside or load)]
+            out["power_w_first_last"] = [pw[0], pw[-1]]
         return out
 
 
@@ -459,7 +468,10 @@ def run_gpu(args, wl):
     achieved = bpu * no * km / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": load_traffic(args.workload) if not (args.km or args.kind or args.mask >= 0) else None,   # measured at the workload's own size only
-                "kernel_ms": k_ms, "bytes_per_unit": bpu, "bytes_per_unit_with_this_librarys_whole_plan": bpu_repo, "units_per_launch": no * km,
+                "kernel_ms": k_ms, "kernel_ms_spread": {"min": min(apply_ms), "median": sorted(apply_ms)[len(apply_ms) // 2], "max": max(apply_ms),
+                                                        "first_quarter_mean": sum(apply_ms[:max(1, len(apply_ms) // 4)]) / max(1, len(apply_ms) // 4),
+                                                        "last_quarter_mean": sum(apply_ms[-max(1, len(apply_ms) // 4):]) / max(1, len(apply_ms) // 4)},
+                "bytes_per_unit": bpu, "bytes_per_unit_with_this_librarys_whole_plan": bpu_repo, "units_per_launch": no * km,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, burst)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "frac_of_nominal_8TBs": achieved / 8000.0}
 
